@@ -1,0 +1,30 @@
+"""Build libigtmpc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m igt_mpc_int_b200.build [--force]
+"""
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(_HERE, "csrc", f) for f in ("igt_abi.cu",)]
+DEPS = SRC + [os.path.join(_HERE, "csrc", f) for f in ("solver_core.cuh", "params_host.hpp")] + \
+       [os.path.join(_HERE, "..", "include", "igt_mpc.h")]
+OUT = os.path.join(_HERE, "lib", "libigtmpc.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build(force=False, verbose=False):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,446 @@
+// igt_abi.cu -- kernels and the extern "C" boundary of libigtmpc.so (see include/igt_mpc.h).
+//
+// Kernels (all hand-written, sm_100a):
+//   solve_kernel<T>       one MPC problem per thread, whole interior-point iLQR on chip + SoA
+//                         workspace in HBM (solver_core.cuh); replaces mpc.py:383-406
+//   rollout_kernel        fp32 Frenet RK4 rollout + analytic Jacobians (compensated state
+//                         accumulation); replaces kinematic_bicycle_model_frenet.py:69-185
+//   rollout_euler_kernel  fp32 Cartesian Euler rollout + Jacobians; kinematic_bicycle_model.py:15-50
+//   eval_kernel           fp64 cost / max-row-violation of given controls; mpc.py:177-373
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/igt_mpc.h"
+#include "solver_core.cuh"
+#include "params_host.hpp"
+
+using namespace igt;
+
+// ------------------------------------------------------------------ device constants ----
+__constant__ DevParams<float> c_Pf;
+__constant__ DevParams<double> c_Pd;
+
+template <typename T> struct ConstP;
+template <> struct ConstP<float> { static __device__ __forceinline__ const DevParams<float> &get() { return c_Pf; } };
+template <> struct ConstP<double> { static __device__ __forceinline__ const DevParams<double> &get() { return c_Pd; } };
+
+// ------------------------------------------------------------------ kernels -------------
+template <typename T>
+__global__ void __launch_bounds__(64) solve_kernel(ProbIO io, T *ws, long B, T *mlp_scratch, int mlp_width)
+{
+    long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const DevParams<T> &P = ConstP<T>::get();
+    solve_problem<T>(P, io, ws, B, p, mlp_scratch ? mlp_scratch + p * 12 * (long)mlp_width : nullptr, mlp_width);
+}
+
+// fp32 rollout with Kahan-compensated accumulation of the RK4 increments (x, y, s reach ~50 m
+// while one sub-step adds ~0.1 m; plain fp32 accumulation loses the 1e-5 target on ~0.5 % of
+// rollouts).  One problem per thread; outputs are AoS as the ABI promises.
+__global__ void __launch_bounds__(128) rollout_kernel(int B, const float *__restrict__ z0,
+                                                      const float *__restrict__ U,
+                                                      const float *__restrict__ curv_, float *__restrict__ Z,
+                                                      float *__restrict__ A, float *__restrict__ Bm)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const DevParams<float> &P = c_Pf;
+    const int N = P.N;
+    float z[NZ], comp[NZ], curv[3] = { curv_[3 * p], curv_[3 * p + 1], curv_[3 * p + 2] };
+#pragma unroll
+    for (int i = 0; i < NZ; i++) { z[i] = z0[(long)p * NZ + i]; comp[i] = 0.f; Z[(long)p * (N + 1) * NZ + i] = z[i]; }
+    const float h = P.h;
+    for (int k = 0; k < N; k++) {
+        float u[2] = { U[((long)p * N + k) * 2], U[((long)p * N + k) * 2 + 1] };
+        if (A) {
+            float zn[NZ], S[NZ][NSEED];
+            rk4_step_sens(P, z, u, curv, zn, S);
+            float *Ak = A + ((long)p * N + k) * NZ * NZ, *Bk = Bm + ((long)p * N + k) * NZ * 2;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+#pragma unroll
+                for (int j = 0; j < NZ; j++) Ak[i * NZ + j] = (i == j && j < 3) ? 1.f : 0.f;
+                Ak[i * NZ + IEY] = S[i][0]; Ak[i * NZ + IEPSI] = S[i][1]; Ak[i * NZ + IV] = S[i][2]; Ak[i * NZ + IPSI] = S[i][3];
+                Bk[i * 2] = S[i][4]; Bk[i * 2 + 1] = S[i][5];
+            }
+        }
+        // compensated value step
+        Slip<float> sl = slip_of(P, u[1]);
+        for (int it = 0; it < P.n_rk; it++) {
+            float zs[NZ], k1[NZ], k2[NZ], k3[NZ], k4[NZ];
+            rhs<float, false>(P, z, u[0], sl, curv, k1, nullptr);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * 0.5f * k1[i];
+            rhs<float, false>(P, zs, u[0], sl, curv, k2, nullptr);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * 0.5f * k2[i];
+            rhs<float, false>(P, zs, u[0], sl, curv, k3, nullptr);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * k3[i];
+            zs[IPSI] = z[IPSI] + h * 0.5f * k3[IPSI];
+            rhs<float, false>(P, zs, u[0], sl, curv, k4, nullptr);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                float inc = h / 6.f * (k1[i] + 2.f * k2[i] + 2.f * k3[i] + k4[i]);
+                float y = inc - comp[i];
+                float t = z[i] + y;
+                comp[i] = (t - z[i]) - y;
+                z[i] = t;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NZ; i++) Z[((long)p * (N + 1) + k + 1) * NZ + i] = z[i];
+    }
+}
+
+__global__ void __launch_bounds__(128) rollout_euler_kernel(int B, const float *__restrict__ z0,
+                                                            const float *__restrict__ U, float *__restrict__ Z,
+                                                            float *__restrict__ A, float *__restrict__ Bm)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const DevParams<float> &P = c_Pf;
+    const int N = P.N;
+    float z[4];
+    for (int i = 0; i < 4; i++) { z[i] = z0[(long)p * 4 + i]; Z[(long)p * (N + 1) * 4 + i] = z[i]; }
+    for (int k = 0; k < N; k++) {
+        float u[2] = { U[((long)p * N + k) * 2], U[((long)p * N + k) * 2 + 1] }, zn[4];
+        euler_step(P, z, u, zn, A ? A + ((long)p * N + k) * 16 : nullptr, A ? Bm + ((long)p * N + k) * 8 : nullptr);
+        for (int i = 0; i < 4; i++) { z[i] = zn[i]; Z[((long)p * (N + 1) + k + 1) * 4 + i] = zn[i]; }
+    }
+}
+
+// fp64 re-roll + cost + max inequality row (reference units) of given controls
+__global__ void __launch_bounds__(128) eval_kernel(long B, const double *__restrict__ x0_, const double *__restrict__ uprev_,
+                                                   const double *__restrict__ curv_, const double *__restrict__ obs_,
+                                                   const double *__restrict__ ctx_, const double *__restrict__ U,
+                                                   double *__restrict__ cost, double *__restrict__ viol,
+                                                   double *__restrict__ Zout, double *mlp_scratch, int mlp_width)
+{
+    long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const DevParams<double> &P = c_Pd;
+    const int N = P.N;
+    double z[NZ], curv[3] = { curv_[3 * p], curv_[3 * p + 1], curv_[3 * p + 2] };
+    double up[2] = { uprev_[2 * p], uprev_[2 * p + 1] };
+    for (int i = 0; i < NZ; i++) z[i] = x0_[p * NZ + i];
+    double s0 = z[IS], J = 0, su = 0, m = 0;
+    const double *obs = obs_ + p * (N + 1) * 2;
+    for (int k = 0; k <= N; k++) {
+        if (Zout) for (int i = 0; i < NZ; i++) Zout[(p * (N + 1) + k) * NZ + i] = z[i];
+        J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
+        m = fmax(m, fabs(z[IEY]) - P.ey_lim);
+        if (k >= 1) {
+            double dx = z[IX] - obs[2 * k], dy = z[IY] - obs[2 * k + 1];
+            m = fmax(m, P.d_min * P.d_min - dx * dx - dy * dy);
+        }
+        if (k == N) break;
+        double u[2] = { U[(p * N + k) * 2], U[(p * N + k) * 2 + 1] };
+        su += u[0] * u[0] + u[1] * u[1];
+        m = fmax(m, fmax(P.v_min - z[IV], z[IV] - P.v_max));
+        m = fmax(m, fmax(P.a_min - u[0], u[0] - P.a_max));
+        m = fmax(m, fabs(u[1]) - P.df_max);
+        m = fmax(m, fabs(u[0] - up[0]) - P.da_max);
+        m = fmax(m, fabs(u[1] - up[1]) - P.ddf_max);
+        if (k == N - 1)
+            for (int q = 0; q < P.n_cinf; q++) m = fmax(m, P.cinf_A[q][0] * z[IV] + P.cinf_A[q][1] * u[0] - P.cinf_b[q]);
+        double zn[NZ];
+        rk4_step(P, z, u, curv, zn);
+        for (int i = 0; i < NZ; i++) z[i] = zn[i];
+        up[0] = u[0]; up[1] = u[1];
+    }
+    J += P.w_u * su;
+    if (ctx_) {
+        TermVal<double> t;
+        double ctx[4] = { ctx_[4 * p], ctx_[4 * p + 1], ctx_[4 * p + 2], ctx_[4 * p + 3] };
+        double *sc = mlp_scratch + p * 12 * (long)mlp_width;
+        mlp_eval_thread(P, z[IS], z[IV], ctx, sc, sc + 6 * mlp_width, mlp_width, t, false);
+        J -= t.V;
+    } else {
+        J -= z[IS] - s0;
+    }
+    cost[p] = J;
+    viol[p] = m;
+}
+
+// ------------------------------------------------------------------ handle --------------
+struct igt_handle {
+    igt_params prm;
+    DevParams<float> Pf;
+    DevParams<double> Pd;
+    bool has_mlp = false;
+    int mlp_width = 0;
+    std::vector<void *> mlp_bufs;      // device weight buffers (both precisions)
+    void *ws = nullptr; size_t ws_bytes = 0;
+    void *mlp_scratch = nullptr; size_t mlp_scratch_bytes = 0;
+    void *stage = nullptr; size_t stage_bytes = 0;     // device staging for *_host calls
+    long long launches = 0;
+    std::string err;
+    int device = 0;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+            return IGT_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+static int grow(igt_handle *h, void **buf, size_t *have, size_t need)
+{
+    if (*have >= need) return IGT_OK;
+    if (*buf) { CK(cudaFree(*buf)); *buf = nullptr; *have = 0; }
+    CK(cudaMalloc(buf, need));
+    *have = need;
+    return IGT_OK;
+}
+
+extern "C" {
+
+const char *igt_version(void) { return "igtmpc 0.1 sm_100a"; }
+
+int igt_default_params(igt_params *p, int precision) { return igt::default_params(p, precision); }
+
+int igt_create(const igt_params *p, igt_handle **out)
+{
+    if (!p || !out) { g_create_err = "null argument"; return IGT_EINVAL; }
+    if (p->N < 2 || p->N > 64 || p->n_rk < 1 || p->n_cinf < 0 || p->n_cinf > IGT_MAX_CINF ||
+        (p->precision != IGT_PREC_F32 && p->precision != IGT_PREC_F64)) {
+        g_create_err = "unsupported N / n_rk / n_cinf / precision";
+        return IGT_EINVAL;
+    }
+    igt_handle *h = new (std::nothrow) igt_handle();
+    if (!h) { g_create_err = "out of memory"; return IGT_EINVAL; }
+    h->prm = *p;
+    fill_dev_params(*p, h->Pf);
+    fill_dev_params(*p, h->Pd);
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("cudaGetDevice: ") + cudaGetErrorString(e) + " (no CUDA device: this library has no CPU path)";
+        delete h;
+        return IGT_ECUDA;
+    }
+    *out = h;
+    return IGT_OK;
+}
+
+void igt_destroy(igt_handle *h)
+{
+    if (!h) return;
+    for (void *b : h->mlp_bufs) cudaFree(b);
+    if (h->ws) cudaFree(h->ws);
+    if (h->mlp_scratch) cudaFree(h->mlp_scratch);
+    if (h->stage) cudaFree(h->stage);
+    delete h;
+}
+
+const char *igt_last_error(const igt_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+long long igt_launch_count(const igt_handle *h) { return h ? h->launches : 0; }
+
+int igt_set_mlp(igt_handle *h, int n_layers, const int *dims, const double *const *W, const double *const *b,
+                const double *Wn, const double *mu_f, double sigma_t, double mu_t)
+{
+    if (!h) return IGT_EINVAL;
+    if (n_layers < 1 || n_layers > IGT_MAX_MLP_LAYERS || !dims || !W || !b || !Wn || !mu_f || dims[0] != 6 ||
+        dims[n_layers] != 1) { h->err = "igt_set_mlp: bad layer description"; return IGT_EINVAL; }
+    for (void *q : h->mlp_bufs) cudaFree(q);
+    h->mlp_bufs.clear();
+    int width = 6;
+    for (int l = 0; l <= n_layers; l++) { if (dims[l] < 1 || dims[l] > 1024) { h->err = "igt_set_mlp: bad width"; return IGT_EINVAL; } if (dims[l] > width) width = dims[l]; }
+    h->mlp_width = width;
+    h->Pf.n_layers = h->Pd.n_layers = n_layers;
+    for (int l = 0; l <= n_layers; l++) h->Pf.dims[l] = h->Pd.dims[l] = dims[l];
+    for (int l = 0; l < n_layers; l++) {
+        size_t nw = (size_t)dims[l] * dims[l + 1], nb = dims[l + 1];
+        std::vector<float> wf(nw), bf(nb);
+        for (size_t i = 0; i < nw; i++) wf[i] = (float)W[l][i];
+        for (size_t i = 0; i < nb; i++) bf[i] = (float)b[l][i];
+        void *dWd, *dbd, *dWf, *dbf;
+        CK(cudaMalloc(&dWd, nw * 8)); h->mlp_bufs.push_back(dWd);
+        CK(cudaMalloc(&dbd, nb * 8)); h->mlp_bufs.push_back(dbd);
+        CK(cudaMalloc(&dWf, nw * 4)); h->mlp_bufs.push_back(dWf);
+        CK(cudaMalloc(&dbf, nb * 4)); h->mlp_bufs.push_back(dbf);
+        CK(cudaMemcpy(dWd, W[l], nw * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dbd, b[l], nb * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dWf, wf.data(), nw * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dbf, bf.data(), nb * 4, cudaMemcpyHostToDevice));
+        h->Pd.W[l] = (const double *)dWd; h->Pd.b[l] = (const double *)dbd;
+        h->Pf.W[l] = (const float *)dWf; h->Pf.b[l] = (const float *)dbf;
+    }
+    for (int i = 0; i < 36; i++) { h->Pd.Wn[i] = Wn[i]; h->Pf.Wn[i] = (float)Wn[i]; }
+    for (int i = 0; i < 6; i++) { h->Pd.mu_f[i] = mu_f[i]; h->Pf.mu_f[i] = (float)mu_f[i]; }
+    h->Pd.sigma_t = sigma_t; h->Pd.mu_t = mu_t; h->Pf.sigma_t = (float)sigma_t; h->Pf.mu_t = (float)mu_t;
+    h->has_mlp = true;
+    return IGT_OK;
+}
+
+static int upload_params(igt_handle *h, cudaStream_t st, bool f32, bool f64)
+{
+    if (f32) CK(cudaMemcpyToSymbolAsync(c_Pf, &h->Pf, sizeof(h->Pf), 0, cudaMemcpyHostToDevice, st));
+    if (f64) CK(cudaMemcpyToSymbolAsync(c_Pd, &h->Pd, sizeof(h->Pd), 0, cudaMemcpyHostToDevice, st));
+    return IGT_OK;
+}
+
+int igt_rollout_dev(igt_handle *h, int B, const float *z0, const float *u, const float *curv, float *z,
+                    float *A, float *Bm, int model, void *stream)
+{
+    if (!h) return IGT_EINVAL;
+    if (B < 0 || !z0 || !u || !z || (model == 0 && !curv) || ((A == nullptr) != (Bm == nullptr)) ||
+        (model != 0 && model != 1)) { h->err = "igt_rollout: bad argument"; return IGT_EINVAL; }
+    if (B == 0) return IGT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_params(h, st, true, false);
+    if (rc) return rc;
+    int bs = 128, gs = (B + bs - 1) / bs;
+    if (model == 0) rollout_kernel<<<gs, bs, 0, st>>>(B, z0, u, curv, z, A, Bm);
+    else rollout_euler_kernel<<<gs, bs, 0, st>>>(B, z0, u, z, A, Bm);
+    h->launches++;
+    CK(cudaGetLastError());
+    return IGT_OK;
+}
+
+int igt_rollout_host(igt_handle *h, int B, const float *z0, const float *u, const float *curv, float *z,
+                     float *A, float *Bm, int model)
+{
+    if (!h) return IGT_EINVAL;
+    if (B < 0 || !z0 || !u || !z || (model == 0 && !curv)) { h->err = "igt_rollout: bad argument"; return IGT_EINVAL; }
+    if (B == 0) return IGT_OK;
+    const int N = h->prm.N, nz = model == 0 ? 7 : 4;
+    size_t n_z0 = (size_t)B * nz, n_u = (size_t)B * N * 2, n_c = (size_t)B * 3, n_z = (size_t)B * (N + 1) * nz;
+    size_t n_A = A ? (size_t)B * N * nz * nz : 0, n_B = A ? (size_t)B * N * nz * 2 : 0;
+    size_t total = (n_z0 + n_u + n_c + n_z + n_A + n_B) * sizeof(float);
+    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    if (rc) return rc;
+    float *d = (float *)h->stage;
+    float *dz0 = d, *du = dz0 + n_z0, *dc = du + n_u, *dz = dc + n_c, *dA = dz + n_z, *dB = dA + n_A;
+    CK(cudaMemcpy(dz0, z0, n_z0 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(du, u, n_u * 4, cudaMemcpyHostToDevice));
+    if (model == 0) CK(cudaMemcpy(dc, curv, n_c * 4, cudaMemcpyHostToDevice));
+    rc = igt_rollout_dev(h, B, dz0, du, dc, dz, A ? dA : nullptr, A ? dB : nullptr, model, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(z, dz, n_z * 4, cudaMemcpyDeviceToHost));
+    if (A) { CK(cudaMemcpy(A, dA, n_A * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(Bm, dB, n_B * 4, cudaMemcpyDeviceToHost)); }
+    return IGT_OK;
+}
+
+int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                  const double *obs_xy, const double *nn_ctx, const double *u_init, double *x, double *u,
+                  double *cost, double *viol, int *status, int *iters, void *stream)
+{
+    if (!h) return IGT_EINVAL;
+    if (B < 0 || !x0 || !u_prev || !curv || !obs_xy || !x || !u || !cost || !viol || !status || !iters) {
+        h->err = "igt_solve: null argument"; return IGT_EINVAL;
+    }
+    if (nn_ctx && !h->has_mlp) { h->err = "igt_solve: nn_ctx given but igt_set_mlp was never called"; return IGT_ENOMLP; }
+    if (B == 0) return IGT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool f64 = h->prm.precision == IGT_PREC_F64;
+    WsLayout L; L.init(h->prm.N, h->prm.n_cinf);
+    size_t esz = f64 ? 8 : 4;
+    int rc = grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * B * esz);
+    if (rc) return rc;
+    if (nn_ctx) {
+        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * B * esz);
+        if (rc) return rc;
+    }
+    rc = upload_params(h, st, !f64, f64);
+    if (rc) return rc;
+    ProbIO io = { x0, u_prev, curv, obs_xy, nn_ctx, u_init, x, u, cost, viol, status, iters };
+    int bs = 64, gs = (B + bs - 1) / bs;
+    if (f64) solve_kernel<double><<<gs, bs, 0, st>>>(io, (double *)h->ws, B, nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width);
+    else solve_kernel<float><<<gs, bs, 0, st>>>(io, (float *)h->ws, B, nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width);
+    h->launches++;
+    CK(cudaGetLastError());
+    return IGT_OK;
+}
+
+int igt_solve_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                   const double *obs_xy, const double *nn_ctx, const double *u_init, double *x, double *u,
+                   double *cost, double *viol, int *status, int *iters)
+{
+    if (!h) return IGT_EINVAL;
+    if (B < 0 || !x0 || !u_prev || !curv || !obs_xy || !x || !u || !cost || !viol || !status || !iters) {
+        h->err = "igt_solve: null argument"; return IGT_EINVAL;
+    }
+    if (B == 0) return IGT_OK;
+    const int N = h->prm.N;
+    size_t nb = (size_t)B;
+    size_t n_x0 = nb * 7, n_up = nb * 2, n_c = nb * 3, n_o = nb * (N + 1) * 2, n_ctx = nn_ctx ? nb * 4 : 0;
+    size_t n_ui = u_init ? nb * N * 2 : 0, n_x = nb * (N + 1) * 7, n_u = nb * N * 2;
+    size_t n_in = n_x0 + n_up + n_c + n_o + n_ctx + n_ui, n_out = n_x + n_u + 2 * nb;
+    size_t total = (n_in + n_out) * 8 + 2 * nb * 4;
+    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    if (rc) return rc;
+    double *d = (double *)h->stage;
+    double *dx0 = d, *dup = dx0 + n_x0, *dc = dup + n_up, *dob = dc + n_c, *dctx = dob + n_o, *dui = dctx + n_ctx;
+    double *dx = dui + n_ui, *du = dx + n_x, *dcost = du + n_u, *dviol = dcost + nb;
+    int *dst = (int *)(dviol + nb), *dit = dst + nb;
+    cudaStream_t st = nullptr;
+    CK(cudaMemcpyAsync(dx0, x0, n_x0 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dup, u_prev, n_up * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dc, curv, n_c * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dob, obs_xy, n_o * 8, cudaMemcpyHostToDevice, st));
+    if (nn_ctx) CK(cudaMemcpyAsync(dctx, nn_ctx, n_ctx * 8, cudaMemcpyHostToDevice, st));
+    if (u_init) CK(cudaMemcpyAsync(dui, u_init, n_ui * 8, cudaMemcpyHostToDevice, st));
+    rc = igt_solve_dev(h, B, dx0, dup, dc, dob, nn_ctx ? dctx : nullptr, u_init ? dui : nullptr, dx, du, dcost, dviol,
+                       dst, dit, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(x, dx, n_x * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(u, du, n_u * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cost, dcost, nb * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(viol, dviol, nb * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, dst, nb * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(iters, dit, nb * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return IGT_OK;
+}
+
+int igt_eval_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                  const double *obs_xy, const double *nn_ctx, const double *u, double *cost, double *viol,
+                  double *z)
+{
+    if (!h) return IGT_EINVAL;
+    if (B < 0 || !x0 || !u_prev || !curv || !obs_xy || !u || !cost || !viol) { h->err = "igt_eval: null argument"; return IGT_EINVAL; }
+    if (nn_ctx && !h->has_mlp) { h->err = "igt_eval: nn_ctx given but igt_set_mlp was never called"; return IGT_ENOMLP; }
+    if (B == 0) return IGT_OK;
+    const int N = h->prm.N;
+    size_t nb = (size_t)B;
+    size_t n_x0 = nb * 7, n_up = nb * 2, n_c = nb * 3, n_o = nb * (N + 1) * 2, n_ctx = nn_ctx ? nb * 4 : 0;
+    size_t n_u = nb * N * 2, n_z = nb * (N + 1) * 7;
+    size_t total = (n_x0 + n_up + n_c + n_o + n_ctx + n_u + n_z + 2 * nb) * 8;
+    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    if (rc) return rc;
+    if (nn_ctx) { rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * B * 8); if (rc) return rc; }
+    double *d = (double *)h->stage;
+    double *dx0 = d, *dup = dx0 + n_x0, *dc = dup + n_up, *dob = dc + n_c, *dctx = dob + n_o, *du = dctx + n_ctx;
+    double *dz = du + n_u, *dcost = dz + n_z, *dviol = dcost + nb;
+    CK(cudaMemcpy(dx0, x0, n_x0 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dup, u_prev, n_up * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc, curv, n_c * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dob, obs_xy, n_o * 8, cudaMemcpyHostToDevice));
+    if (nn_ctx) CK(cudaMemcpy(dctx, nn_ctx, n_ctx * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(du, u, n_u * 8, cudaMemcpyHostToDevice));
+    rc = upload_params(h, nullptr, false, true);
+    if (rc) return rc;
+    int bs = 128, gs = (B + bs - 1) / bs;
+    eval_kernel<<<gs, bs>>>(B, dx0, dup, dc, dob, nn_ctx ? dctx : nullptr, du, dcost, dviol, dz,
+                            nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(cost, dcost, nb * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(viol, dviol, nb * 8, cudaMemcpyDeviceToHost));
+    if (z) CK(cudaMemcpy(z, dz, n_z * 8, cudaMemcpyDeviceToHost));
+    return IGT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,984 @@
+// solver_core.cuh -- per-problem interior-point iLQR for the IGT-MPC NLP, one problem per thread.
+//
+// Replaces the arithmetic behind reference mpc.py:383-406 (opti.solve() -> CasADi -> IPOPT).
+// The NLP is the one assembled in mpc.py:147-160:
+//   dynamics   4-substep RK4 Frenet kinematic bicycle, common/kinematic_bicycle_model_frenet.py:69-185
+//   rows       mpc.py:177-180 (terminal set), :223-226 (collision), :296-321 (ey, rate, box)
+//   cost       mpc.py:356-373
+// Method (DESIGN.md "solver"): single shooting on u with the previous input appended to the
+// state (zeta = [z; u_prev]) so that the rate rows become stage-local; per iteration
+//   sweep 1  forward sensitivities of every stage (6 seeds through the RK stages)
+//   sweep 2  adjoint recursion -> KKT residuals -> barrier parameter update
+//   sweep 3  Riccati recursion on the perturbed KKT system (slack y, multiplier s per row)
+//   sweep 4+ closed-loop nonlinear forward passes with fraction-to-boundary and a
+//            (barrier cost, infeasibility) acceptance test.
+// All per-problem state lives in a struct-of-arrays workspace in HBM (element e of problem p
+// at base[e * stride + p]) so that the 32 problems of a warp read and write 32 consecutive
+// words; the small matrices of one stage live in registers.
+//
+// Everything here is __host__ __device__ so that tests can run the very same code on the CPU
+// (tests/hostsim) -- the product only ever launches it from kernels.cu.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define IGT_HD __host__ __device__ __forceinline__
+#define IGT_HDN __host__ __device__ __noinline__
+#else
+#define IGT_HD inline
+#define IGT_HDN
+#endif
+
+namespace igt {
+
+constexpr int NZ = 7, NA = 9, NW = 11, NSEED = 6;
+enum { IX = 0, IY, IS, IEY, IEPSI, IV, IPSI, IPA, IPD, IUA, IUD };
+constexpr int MAX_CINF = 128;
+constexpr int MAX_MLP_LAYERS = 5;
+constexpr int N_GUESS = 5;
+
+template <typename T>
+struct DevParams {
+    int N, n_rk, n_cinf, max_iter, n_alpha, second_order, n_layers;
+    int dims[MAX_MLP_LAYERS + 1];
+    T dt, h, l_r, lsum, inv_lr, rho;
+    T v_min, v_max, a_min, a_max, df_max, ey_lim, da_max, ddf_max, d_min, w_u;
+    T tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min;
+    T reg_min, reg_up, reg_down, reg_max, eps_phi, gamma_theta, theta_small;
+    T cinf_A[MAX_CINF][2], cinf_b[MAX_CINF];
+    T Wn[36], mu_f[6], sigma_t, mu_t;
+    const T *W[MAX_MLP_LAYERS], *b[MAX_MLP_LAYERS];   // device pointers, row-major [out][in]
+};
+
+// ------------------------------------------------------------------ workspace ----------
+// Row bookkeeping: stage 0 carries the 8 input rows; stage k >= 1 carries 5 state rows
+// (v hi/lo, ey hi/lo, collision) + 8 input rows (a hi/lo, df hi/lo, rate a +-, rate df +-);
+// stage N-1 additionally the n_cinf terminal-set rows; the terminal node 3 rows.
+IGT_HD int row_off(int N, int n_cinf, int k)
+{
+    if (k == 0) return 0;
+    int o = 8 + 13 * (k - 1);
+    if (k == N) o += n_cinf;
+    return o;
+}
+IGT_HD int row_total(int N, int n_cinf) { return row_off(N, n_cinf, N) + 3; }
+
+struct WsLayout {
+    int N, M;
+    int oZ[2], oU[2], oY[2], oS[2], oSens, oLam, oKu, oKK, total;
+    IGT_HD void init(int N_, int n_cinf)
+    {
+        N = N_;
+        M = row_total(N, n_cinf);
+        int o = 0;
+        for (int b = 0; b < 2; b++) { oZ[b] = o; o += NZ * (N + 1); }
+        for (int b = 0; b < 2; b++) { oU[b] = o; o += 2 * N; }
+        for (int b = 0; b < 2; b++) { oY[b] = o; o += M; }
+        for (int b = 0; b < 2; b++) { oS[b] = o; o += M; }
+        oSens = o; o += NZ * NSEED * N;
+        oLam = o;  o += NZ * (N + 1);
+        oKu = o;   o += 2 * N;
+        oKK = o;   o += 2 * NA * N;
+        total = o;
+    }
+};
+
+template <typename T>
+struct Ws {
+    T *base;
+    long stride;    // number of problems in the launch
+    long p;         // this problem
+    WsLayout L;
+    IGT_HD T &at(int e) const { return base[(long)e * stride + p]; }
+    IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ[b] + k * NZ + i); }
+    IGT_HD T &U(int b, int k, int i) const { return at(L.oU[b] + k * 2 + i); }
+    IGT_HD T &Y(int b, int r) const { return at(L.oY[b] + r); }
+    IGT_HD T &S(int b, int r) const { return at(L.oS[b] + r); }
+    IGT_HD T &Sens(int k, int i, int j) const { return at(L.oSens + (k * NZ + i) * NSEED + j); }
+    IGT_HD T &Lam(int k, int i) const { return at(L.oLam + k * NZ + i); }
+    IGT_HD T &ku(int k, int i) const { return at(L.oKu + k * 2 + i); }
+    IGT_HD T &KK(int k, int i, int j) const { return at(L.oKK + (k * 2 + i) * NA + j); }
+};
+
+// problem inputs / outputs: batch-major AoS arrays exactly as the C ABI receives them
+struct ProbIO {
+    const double *x0, *u_prev, *curv, *obs, *ctx, *u_init;   // [B,7] [B,2] [B,3] [B,N+1,2] [B,4] [B,N,2]
+    double *x, *u, *cost, *viol;
+    int *status, *iters;
+};
+
+// ------------------------------------------------------------------ dynamics -----------
+template <typename T>
+struct Slip { T beta, dbeta, sb, cb; };
+
+template <typename T>
+IGT_HD Slip<T> slip_of(const DevParams<T> &P, T df)
+{   // kinematic_bicycle_model_frenet.py:72
+    Slip<T> r;
+    T t = tan(df);
+    r.beta = atan(P.rho * t);
+    r.dbeta = P.rho * (T(1) + t * t) / (T(1) + P.rho * P.rho * t * t);
+    r.sb = sin(r.beta);
+    r.cb = cos(r.beta);
+    return r;
+}
+
+template <typename T>
+IGT_HD T curvature(T s, T b0, T b1, T kv)
+{   // casadi pw_const, mpc.py:199: K = kv*(s>=b0) - kv*(s>=b1), zero derivative
+    return (s >= b0 ? kv : T(0)) - (s >= b1 ? kv : T(0));
+}
+
+// zdot (planner order) and, if JAC, the 13 state + 6 steering partials
+template <typename T>
+struct RhsJac { T s_ey, s_epsi, s_v, s_d, ey_epsi, ey_v, ey_d, e_ey, e_epsi, e_v, e_d, x_v, x_psi, x_d, y_v, y_psi, y_d, p_v, p_d; };
+
+template <typename T, bool JAC>
+IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const T *curv, T *zd, RhsJac<T> *J)
+{   // kinematic_bicycle_model_frenet.py:71-91
+    T ey = z[IEY], epsi = z[IEPSI], v = z[IV], psi = z[IPSI];
+    T K = curvature(z[IS], curv[0], curv[1], curv[2]);
+    T c1 = cos(sl.beta + epsi), s1 = sin(sl.beta + epsi);
+    T cp = cos(psi + sl.beta), sp = sin(psi + sl.beta);
+    T iden = T(1) / (T(1) - K * ey);
+    T sdot = v * c1 * iden;
+    T yaw = v * sl.sb * P.inv_lr;
+    zd[IS] = sdot;
+    zd[IEY] = v * s1;
+    zd[IEPSI] = yaw - sdot * K;
+    zd[IV] = a;
+    zd[IX] = v * cp;
+    zd[IY] = v * sp;
+    zd[IPSI] = yaw;
+    if (JAC) {
+        T db = sl.dbeta;
+        J->s_ey = sdot * K * iden;
+        J->s_epsi = -v * s1 * iden;
+        J->s_v = c1 * iden;
+        J->s_d = J->s_epsi * db;
+        J->ey_epsi = v * c1; J->ey_v = s1; J->ey_d = v * c1 * db;
+        J->e_ey = -K * J->s_ey; J->e_epsi = -K * J->s_epsi;
+        J->e_v = sl.sb * P.inv_lr - K * J->s_v;
+        J->e_d = (v * sl.cb * P.inv_lr - K * J->s_epsi) * db;
+        J->x_v = cp; J->x_psi = -v * sp; J->x_d = -v * sp * db;
+        J->y_v = sp; J->y_psi = v * cp; J->y_d = v * cp * db;
+        J->p_v = sl.sb * P.inv_lr; J->p_d = v * sl.cb * P.inv_lr * db;
+    }
+}
+
+// one MPC step, values only.  k4 evaluates xdot, ydot at psi + h/2*k3[psi]
+// (kinematic_bicycle_model_frenet.py:111) -- reproduced on purpose.
+template <typename T>
+IGT_HD void rk4_step(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn)
+{
+    const T h = P.h;
+    Slip<T> sl = slip_of(P, u[1]);
+    T z[NZ], zs[NZ], k1[NZ], k2[NZ], k3[NZ], k4[NZ];
+#pragma unroll
+    for (int i = 0; i < NZ; i++) z[i] = z0[i];
+    for (int it = 0; it < P.n_rk; it++) {
+        rhs<T, false>(P, z, u[0], sl, curv, k1, nullptr);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * T(0.5) * k1[i];
+        rhs<T, false>(P, zs, u[0], sl, curv, k2, nullptr);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * T(0.5) * k2[i];
+        rhs<T, false>(P, zs, u[0], sl, curv, k3, nullptr);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * k3[i];
+        zs[IPSI] = z[IPSI] + h * T(0.5) * k3[IPSI];
+        rhs<T, false>(P, zs, u[0], sl, curv, k4, nullptr);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) z[i] += h / T(6) * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NZ; i++) zn[i] = z[i];
+}
+
+// tangent of one RHS evaluation: dk[7][6] from stage tangents Ts (rows ey, epsi, v, psi used)
+template <typename T>
+IGT_HD void rhs_tangent(const RhsJac<T> &J, const T (*Ts)[NSEED], T (*dk)[NSEED])
+{
+#pragma unroll
+    for (int j = 0; j < NSEED; j++) {
+        T tey = Ts[IEY][j], tep = Ts[IEPSI][j], tv = Ts[IV][j], tp = Ts[IPSI][j];
+        dk[IS][j] = J.s_ey * tey + J.s_epsi * tep + J.s_v * tv;
+        dk[IEY][j] = J.ey_epsi * tep + J.ey_v * tv;
+        dk[IEPSI][j] = J.e_ey * tey + J.e_epsi * tep + J.e_v * tv;
+        dk[IV][j] = T(0);
+        dk[IX][j] = J.x_v * tv + J.x_psi * tp;
+        dk[IY][j] = J.y_v * tv + J.y_psi * tp;
+        dk[IPSI][j] = J.p_v * tv;
+    }
+    dk[IV][4] = T(1);
+    dk[IS][5] += J.s_d; dk[IEY][5] += J.ey_d; dk[IEPSI][5] += J.e_d;
+    dk[IX][5] += J.x_d; dk[IY][5] += J.y_d; dk[IPSI][5] += J.p_d;
+}
+
+// one MPC step with sensitivities w.r.t. the 6 seeds (ey, epsi, v, psi, a, df): S[7][6].
+// dF/dx = e_x, dF/dy = e_y, dF/ds = e_s (dK/ds == 0) complete the Jacobian.
+template <typename T>
+IGT_HD void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn, T (*S)[NSEED])
+{
+    const T h = P.h;
+    Slip<T> sl = slip_of(P, u[1]);
+    T z[NZ], zs[NZ], k[NZ], kacc[NZ];
+    T Ts[NZ][NSEED], dk[NZ][NSEED], dacc[NZ][NSEED];
+    RhsJac<T> J;
+#pragma unroll
+    for (int i = 0; i < NZ; i++) {
+        z[i] = z0[i];
+#pragma unroll
+        for (int j = 0; j < NSEED; j++) S[i][j] = T(0);
+    }
+    S[IEY][0] = T(1); S[IEPSI][1] = T(1); S[IV][2] = T(1); S[IPSI][3] = T(1);
+    for (int it = 0; it < P.n_rk; it++) {
+        // k1
+        rhs<T, true>(P, z, u[0], sl, curv, k, &J);
+        rhs_tangent(J, S, dk);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) {
+            kacc[i] = k[i];
+            zs[i] = z[i] + h * T(0.5) * k[i];
+#pragma unroll
+            for (int j = 0; j < NSEED; j++) { dacc[i][j] = dk[i][j]; Ts[i][j] = S[i][j] + h * T(0.5) * dk[i][j]; }
+        }
+        // k2
+        rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
+        rhs_tangent(J, Ts, dk);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) {
+            kacc[i] += T(2) * k[i];
+            zs[i] = z[i] + h * T(0.5) * k[i];
+#pragma unroll
+            for (int j = 0; j < NSEED; j++) { dacc[i][j] += T(2) * dk[i][j]; Ts[i][j] = S[i][j] + h * T(0.5) * dk[i][j]; }
+        }
+        // k3
+        rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
+        rhs_tangent(J, Ts, dk);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) {
+            kacc[i] += T(2) * k[i];
+            T cf = (i == IPSI) ? T(0.5) : T(1);     // the k4 psi quirk
+            zs[i] = z[i] + h * cf * k[i];
+#pragma unroll
+            for (int j = 0; j < NSEED; j++) { dacc[i][j] += T(2) * dk[i][j]; Ts[i][j] = S[i][j] + h * cf * dk[i][j]; }
+        }
+        // k4
+        rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
+        rhs_tangent(J, Ts, dk);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) {
+            z[i] += h / T(6) * (kacc[i] + k[i]);
+#pragma unroll
+            for (int j = 0; j < NSEED; j++) S[i][j] += h / T(6) * (dacc[i][j] + dk[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NZ; i++) zn[i] = z[i];
+}
+
+// Cartesian Euler model, z = (x, y, psi, v): kinematic_bicycle_model.py:27-31
+template <typename T>
+IGT_HD void euler_step(const DevParams<T> &P, const T *z, const T *u, T *zn, T *A, T *B)
+{
+    T x = z[0], y = z[1], psi = z[2], v = z[3], dt = P.dt;
+    Slip<T> sl = slip_of(P, u[1]);
+    T lsum = P.lsum, t = tan(u[1]);
+    T cp = cos(psi + sl.beta), sp = sin(psi + sl.beta);
+    zn[0] = x + dt * v * cp;
+    zn[1] = y + dt * v * sp;
+    zn[2] = psi + dt * (v * sl.cb / lsum * t);
+    zn[3] = v + dt * u[0];
+    if (A) {
+        for (int i = 0; i < 16; i++) A[i] = T(0);
+        for (int i = 0; i < 8; i++) B[i] = T(0);
+        A[0] = A[5] = A[10] = A[15] = T(1);
+        A[2] = -dt * v * sp; A[3] = dt * cp;
+        A[6] = dt * v * cp;  A[7] = dt * sp;
+        A[11] = dt * sl.cb / lsum * t;
+        B[1] = -dt * v * sp * sl.dbeta;
+        B[3] = dt * v * cp * sl.dbeta;
+        B[5] = dt * v / lsum * (-sl.sb * sl.dbeta * t + sl.cb * (T(1) + t * t));
+        B[6] = dt;
+    }
+}
+
+// ------------------------------------------------------------------ value term ---------
+template <typename T>
+struct TermVal { T V, gs, gv, Hss, Hsv, Hvv; };
+
+// gt_mpc terminal value (mpc.py:326-354, :367-369; model.py:14-67) on CUDA cores, one
+// problem per thread: value + first and second forward tangents in (s_N, v_N).
+// Scratch: two [6][width] slabs of the caller's workspace.
+template <typename T>
+IGT_HDN void mlp_eval_thread(const DevParams<T> &P, T sN, T vN, const T *ctx, T *ha, T *hb, int width,
+                             TermVal<T> &out, bool want_deriv)
+{
+    T xN[6] = { ctx[0], ctx[1], ctx[2], sN - ctx[0], vN - ctx[1], ctx[3] - ctx[2] };
+    const int R = want_deriv ? 6 : 1;
+    for (int i = 0; i < 6; i++) {
+        T acc = T(0);
+        for (int j = 0; j < 6; j++) acc += P.Wn[i * 6 + j] * (xN[j] - P.mu_f[j]);
+        ha[0 * width + i] = acc;
+        if (want_deriv) {
+            ha[1 * width + i] = P.Wn[i * 6 + 3];
+            ha[2 * width + i] = P.Wn[i * 6 + 4];
+            ha[3 * width + i] = ha[4 * width + i] = ha[5 * width + i] = T(0);
+        }
+    }
+    for (int l = 0; l < P.n_layers; l++) {
+        int nin = P.dims[l], nout = P.dims[l + 1];
+        const T *W = P.W[l], *b = P.b[l];
+        for (int o = 0; o < nout; o++) {
+            T acc[6] = { b[o], T(0), T(0), T(0), T(0), T(0) };
+            for (int i = 0; i < nin; i++) {
+                T w = W[(long)o * nin + i];
+                for (int r = 0; r < R; r++) acc[r] += w * ha[r * width + i];
+            }
+            if (l < P.n_layers - 1) {
+                T y = tanh(acc[0]), d1 = T(1) - y * y, d2 = T(-2) * y * d1;
+                hb[0 * width + o] = y;
+                if (want_deriv) {
+                    T ts = acc[1], tv = acc[2];
+                    hb[1 * width + o] = d1 * ts;
+                    hb[2 * width + o] = d1 * tv;
+                    hb[3 * width + o] = d1 * acc[3] + d2 * ts * ts;
+                    hb[4 * width + o] = d1 * acc[4] + d2 * ts * tv;
+                    hb[5 * width + o] = d1 * acc[5] + d2 * tv * tv;
+                }
+            } else {
+                for (int r = 0; r < R; r++) hb[r * width + o] = acc[r];
+            }
+        }
+        T *t = ha; ha = hb; hb = t;
+    }
+    out.V = ha[0] * P.sigma_t + P.mu_t;
+    if (want_deriv) {
+        out.gs = ha[1 * width] * P.sigma_t; out.gv = ha[2 * width] * P.sigma_t;
+        out.Hss = ha[3 * width] * P.sigma_t; out.Hsv = ha[4 * width] * P.sigma_t; out.Hvv = ha[5 * width] * P.sigma_t;
+    } else {
+        out.gs = out.gv = out.Hss = out.Hsv = out.Hvv = T(0);
+    }
+}
+
+// ------------------------------------------------------------------ rows ---------------
+// visit every inequality row of stage k (k == N: terminal node) in workspace order.
+// f(r, c, i0, g0, i1, g1, hxx, hxy, hyy): value, up to two gradient entries in w = (zeta, u)
+// (i1 < 0: single entry), 2x2 Hessian block on (x, y) (collision row, else zeros).
+template <typename T, typename F>
+IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, const T *u, T ox, T oy, F &&f)
+{
+    const T Z0 = T(0);
+    int r = 0;
+    if (k >= 1) {
+        if (k < P.N) {
+            f(r++, z[IV] - P.v_max, IV, T(1), -1, Z0, Z0, Z0, Z0);      // mpc.py:317
+            f(r++, P.v_min - z[IV], IV, T(-1), -1, Z0, Z0, Z0, Z0);     // mpc.py:316
+        }
+        f(r++, z[IEY] - P.ey_lim, IEY, T(1), -1, Z0, Z0, Z0, Z0);      // mpc.py:298
+        f(r++, -P.ey_lim - z[IEY], IEY, T(-1), -1, Z0, Z0, Z0, Z0);    // mpc.py:299
+        {   // mpc.py:226 in the equivalent distance form d_min - |p - o| <= 0
+            T dx = z[IX] - ox, dy = z[IY] - oy;
+            T dist = sqrt(dx * dx + dy * dy);
+            dist = dist < T(1e-9) ? T(1e-9) : dist;
+            T id = T(1) / dist, nx = dx * id, ny = dy * id;
+            f(r++, P.d_min - dist, IX, -nx, IY, -ny, -(T(1) - nx * nx) * id, nx * ny * id, -(T(1) - ny * ny) * id);
+        }
+    }
+    if (k == P.N) return;
+    f(r++, u[0] - P.a_max, IUA, T(1), -1, Z0, Z0, Z0, Z0);             // mpc.py:319
+    f(r++, P.a_min - u[0], IUA, T(-1), -1, Z0, Z0, Z0, Z0);            // mpc.py:318
+    f(r++, u[1] - P.df_max, IUD, T(1), -1, Z0, Z0, Z0, Z0);            // mpc.py:321
+    f(r++, -P.df_max - u[1], IUD, T(-1), -1, Z0, Z0, Z0, Z0);          // mpc.py:320
+    T da = u[0] - up[0], dd = u[1] - up[1];
+    f(r++, da - P.da_max, IPA, T(-1), IUA, T(1), Z0, Z0, Z0);          // mpc.py:303-311
+    f(r++, -da - P.da_max, IPA, T(1), IUA, T(-1), Z0, Z0, Z0);
+    f(r++, dd - P.ddf_max, IPD, T(-1), IUD, T(1), Z0, Z0, Z0);
+    f(r++, -dd - P.ddf_max, IPD, T(1), IUD, T(-1), Z0, Z0, Z0);
+    if (k == P.N - 1)
+        for (int m = 0; m < P.n_cinf; m++)                              // mpc.py:177-180
+            f(r++, P.cinf_A[m][0] * z[IV] + P.cinf_A[m][1] * u[0] - P.cinf_b[m], IV, P.cinf_A[m][0], IUA,
+              P.cinf_A[m][1], Z0, Z0, Z0);
+}
+
+// symmetric 11x11 / 9x9 storage (upper triangle, row-major)
+IGT_HD constexpr int sym11(int i, int j) { return i <= j ? i * NW - i * (i - 1) / 2 + (j - i) : j * NW - j * (j - 1) / 2 + (i - j); }
+IGT_HD constexpr int sym9(int i, int j) { return i <= j ? i * NA - i * (i - 1) / 2 + (j - i) : j * NA - j * (j - 1) / 2 + (i - j); }
+
+// structural non-zeros of F = d zeta+ / d w  (rows: zeta+ [9], cols: w [11])
+IGT_HD constexpr bool fmask(int a, int j)
+{
+    return (a == IX && (j == IX || j == IV || j == IPSI || j == IUA || j == IUD)) ||
+           (a == IY && (j == IY || j == IV || j == IPSI || j == IUA || j == IUD)) ||
+           (a == IS && (j == IS || j == IEY || j == IEPSI || j == IV || j == IUA || j == IUD)) ||
+           (a == IEY && (j == IEY || j == IEPSI || j == IV || j == IUA || j == IUD)) ||
+           (a == IEPSI && (j == IEY || j == IEPSI || j == IV || j == IUA || j == IUD)) ||
+           (a == IV && (j == IV || j == IUA)) ||
+           (a == IPSI && (j == IV || j == IPSI || j == IUA || j == IUD)) ||
+           (a == IPA && j == IUA) || (a == IPD && j == IUD);
+}
+
+// build F[9][11] from the stored sensitivities S[7][6]
+template <typename T>
+IGT_HD void build_F(const DevParams<T> &P, const T (*S)[NSEED], T (*F)[NW])
+{
+#pragma unroll
+    for (int a = 0; a < NA; a++)
+#pragma unroll
+        for (int j = 0; j < NW; j++) F[a][j] = T(0);
+    F[IX][IX] = T(1); F[IY][IY] = T(1); F[IS][IS] = T(1);
+#pragma unroll
+    for (int a = 0; a < NZ; a++) {
+        F[a][IEY] = S[a][0]; F[a][IEPSI] = S[a][1]; F[a][IV] = S[a][2]; F[a][IPSI] = S[a][3];
+        F[a][IUA] = S[a][4]; F[a][IUD] = S[a][5];
+    }
+    F[IPA][IUA] = T(1); F[IPD][IUD] = T(1);
+}
+
+// dt * Hess(lambda . f) on (ey, epsi, v, psi, df), added into the symmetric w-space Hessian
+template <typename T>
+IGT_HD void add_dyn_hessian(const DevParams<T> &P, const T *z, T df, const T *curv, const T *lam, T *H)
+{
+    T ey = z[IEY], epsi = z[IEPSI], v = z[IV], psi = z[IPSI];
+    T K = curvature(z[IS], curv[0], curv[1], curv[2]);
+    T t = tan(df), rho = P.rho;
+    T beta = atan(rho * t), q = T(1) + rho * rho * t * t;
+    T b1 = rho * (T(1) + t * t) / q;
+    T b2 = rho * T(2) * t * (T(1) - rho * rho) / (q * q) * (T(1) + t * t);
+    T th = beta + epsi, ph = psi + beta;
+    T cth = cos(th), sth = sin(th), cph = cos(ph), sph = sin(ph), cb = cos(beta), sb = sin(beta);
+    T iD = T(1) / (T(1) - K * ey);
+    T m = lam[IS] - K * lam[IEPSI], n = (lam[IEPSI] + lam[IPSI]) * P.inv_lr;
+    T ley = lam[IEY], lx = lam[IX], ly = lam[IY];
+    T G_ey = m * cth * K * iD * iD;
+    T G_epsi = -m * sth * iD + ley * cth;
+    T G_psi = -lx * sph + ly * cph;
+    T G_b = G_epsi + n * cb + G_psi;
+    T G_eyey = m * cth * T(2) * K * K * iD * iD * iD;
+    T G_eyepsi = -m * sth * K * iD * iD;
+    T G_epsiepsi = -m * cth * iD - ley * sth;
+    T G_psipsi = -lx * cph - ly * sph;
+    T G_bb = G_epsiepsi - n * sb + G_psipsi;
+    T dt = P.dt;
+    H[sym11(IEY, IEY)] += dt * v * G_eyey;
+    H[sym11(IEY, IEPSI)] += dt * v * G_eyepsi;
+    H[sym11(IEPSI, IEPSI)] += dt * v * G_epsiepsi;
+    H[sym11(IPSI, IPSI)] += dt * v * G_psipsi;
+    H[sym11(IEY, IV)] += dt * G_ey;
+    H[sym11(IEPSI, IV)] += dt * G_epsi;
+    H[sym11(IV, IPSI)] += dt * G_psi;
+    H[sym11(IEY, IUD)] += dt * v * G_eyepsi * b1;
+    H[sym11(IEPSI, IUD)] += dt * v * G_epsiepsi * b1;
+    H[sym11(IPSI, IUD)] += dt * v * G_psipsi * b1;
+    H[sym11(IV, IUD)] += dt * G_b * b1;
+    H[sym11(IUD, IUD)] += dt * v * (G_bb * b1 * b1 + G_b * b2);
+}
+
+// ------------------------------------------------------------------ the solver ---------
+template <typename T>
+struct Solver {
+    const DevParams<T> &P;
+    Ws<T> w;
+    T x0[NZ], uprev[2], curv[3], ctx[4];
+    const double *obs;        // this problem's [N+1][2] forecast (AoS, read-only)
+    bool gt;                  // gt_mpc terminal cost
+    T *mlp_scratch;           // [2][6][width] when gt (per-thread slab), else null
+    int mlp_width;
+    // iteration state
+    int cur;                  // buffer holding the current iterate
+    int status, iters, ls, need_back;   // need_back: 2 = full backward, 1 = Riccati only, 0 = none
+    bool done;
+    T mu, reg, alpha, Jcur, lgcur, thetacur, phi;
+    T stat, rp, s_max, sy_min, sy_max;
+    TermVal<T> tcur, tcand;
+    T Jcand, lgcand, thetacand;   // trial quantities (without the terminal value term)
+    bool trial_ok;
+
+    IGT_HD Solver(const DevParams<T> &P_) : P(P_) {}
+
+    IGT_HD T ox(int k) const { return T(obs[2 * k]); }
+    IGT_HD T oy(int k) const { return T(obs[2 * k + 1]); }
+
+    // terminal value -(cost contribution): 'mpc' V = s_N - s_0 ; 'gt_mpc' V = MLP
+    IGT_HD void terminal_value(T sN, T vN, TermVal<T> &t, bool want_deriv)
+    {
+        if (!gt) {
+            t.V = sN - x0[IS]; t.gs = T(1); t.gv = T(0); t.Hss = t.Hsv = t.Hvv = T(0);
+        } else {
+            mlp_eval_thread(P, sN, vN, ctx, mlp_scratch, mlp_scratch + 6 * mlp_width, mlp_width, t, want_deriv);
+        }
+    }
+
+    IGT_HD void load_z(int b, int k, T *z) const
+    {
+#pragma unroll
+        for (int i = 0; i < NZ; i++) z[i] = w.Z(b, k, i);
+    }
+    IGT_HD void load_up(int b, int k, T *up) const
+    {
+        if (k == 0) { up[0] = uprev[0]; up[1] = uprev[1]; }
+        else { up[0] = w.U(b, k - 1, 0); up[1] = w.U(b, k - 1, 1); }
+    }
+
+    // tracking controller rollout towards cruise speed vt into buffer b; returns the merit
+    IGT_HD T guess_rollout(int b, T vt)
+    {
+        const int N = P.N;
+        T z[NZ], up[2] = { uprev[0], uprev[1] };
+        T J = T(0), su = T(0), viol = T(0);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) { z[i] = x0[i]; w.Z(b, 0, i) = z[i]; }
+        J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
+        for (int k = 0; k < N; k++) {
+            T K = curvature(z[IS], curv[0], curv[1], curv[2]);
+            T a = T(0.5) * (vt - z[IV]);
+            a = fmin(fmax(a, up[0] - P.da_max), up[0] + P.da_max);
+            a = fmin(fmax(a, P.a_min), P.a_max);
+            T dff = atan(T(2) * tan(asin(K * P.l_r)));
+            T d = dff - T(0.3) * z[IEY] - T(0.8) * z[IEPSI];
+            d = fmin(fmax(d, up[1] - P.ddf_max), up[1] + P.ddf_max);
+            d = fmin(fmax(d, -P.df_max), P.df_max);
+            T u[2] = { a, d };
+            w.U(b, k, 0) = a; w.U(b, k, 1) = d;
+            su += a * a + d * d;
+            if (k == N - 1)
+                for (int m = 0; m < P.n_cinf; m++)
+                    viol += fmax(T(0), P.cinf_A[m][0] * z[IV] + P.cinf_A[m][1] * a - P.cinf_b[m]);
+            T zn[NZ];
+            rk4_step(P, z, u, curv, zn);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) { z[i] = zn[i]; w.Z(b, k + 1, i) = zn[i]; }
+            up[0] = a; up[1] = d;
+            J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
+            if (k + 1 < N) viol += fmax(T(0), z[IV] - P.v_max) + fmax(T(0), P.v_min - z[IV]);
+            viol += fmax(T(0), fabs(z[IEY]) - P.ey_lim);
+            T dx = z[IX] - ox(k + 1), dy = z[IY] - oy(k + 1);
+            viol += fmax(T(0), P.d_min - sqrt(dx * dx + dy * dy));
+        }
+        J += P.w_u * su - (z[IS] - x0[IS]);
+        return J + T(100) * viol;
+    }
+
+    // load inputs, pre-check x0, build the initial iterate.  Returns false if finished already.
+    IGT_HD bool init(const ProbIO &io, long p, bool has_ctx, bool has_uinit)
+    {
+        const int N = P.N;
+        for (int i = 0; i < NZ; i++) x0[i] = T(io.x0[p * NZ + i]);
+        uprev[0] = T(io.u_prev[p * 2]); uprev[1] = T(io.u_prev[p * 2 + 1]);
+        for (int i = 0; i < 3; i++) curv[i] = T(io.curv[p * 3 + i]);
+        obs = io.obs + p * (N + 1) * 2;
+        gt = has_ctx;
+        if (gt) for (int i = 0; i < 4; i++) ctx[i] = T(io.ctx[p * 4 + i]);
+        cur = 0; status = 1; iters = 0; ls = 0; need_back = 2; done = false;
+        mu = P.mu0; reg = T(0); alpha = T(1);
+        {   // rows on x0 alone: mpc.py:316-317 and :298-299 at k = 0
+            T tol = T(1e-9);
+            if (!(x0[IV] >= P.v_min - tol && x0[IV] <= P.v_max + tol && fabs(x0[IEY]) <= P.ey_lim + tol)) {
+                status = 2; done = true;
+                return false;
+            }
+        }
+        if (has_uinit) {
+            T z[NZ];
+            for (int i = 0; i < NZ; i++) { z[i] = x0[i]; w.Z(0, 0, i) = z[i]; }
+            for (int k = 0; k < N; k++) {
+                T u[2] = { T(io.u_init[(p * N + k) * 2]), T(io.u_init[(p * N + k) * 2 + 1]) }, zn[NZ];
+                w.U(0, k, 0) = u[0]; w.U(0, k, 1) = u[1];
+                rk4_step(P, z, u, curv, zn);
+                for (int i = 0; i < NZ; i++) { z[i] = zn[i]; w.Z(0, k + 1, i) = zn[i]; }
+            }
+        } else {
+            // cold-start rule: best of N_GUESS tracking rollouts (DESIGN.md "initial guess")
+            const T speeds[N_GUESS] = { T(5.0), T(3.5), T(2.0), T(1.0), T(0.0) };
+            T best = guess_rollout(0, speeds[0]);
+            int bestg = 0;
+            for (int g = 1; g < N_GUESS; g++) {
+                T m = guess_rollout(1, speeds[g]);
+                if (m < best) { best = m; bestg = g; }
+            }
+            if (bestg != 0) guess_rollout(0, speeds[bestg]);
+        }
+        // slacks / multipliers, J, sum log y, theta of the initial iterate
+        T J = T(0), su = T(0), lg = T(0), th = T(0);
+        for (int k = 0; k <= N; k++) {
+            T z[NZ], up[2], u[2] = { T(0), T(0) };
+            load_z(0, k, z); load_up(0, k, up);
+            if (k < N) { u[0] = w.U(0, k, 0); u[1] = w.U(0, k, 1); su += u[0] * u[0] + u[1] * u[1]; }
+            J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
+            int o = row_off(N, P.n_cinf, k);
+            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int, T, int, T, T, T, T) {
+                T y = fmax(-c, P.y_init_min);
+                w.Y(0, o + r) = y;
+                w.S(0, o + r) = mu / y;
+                lg += log(y);
+                th += fabs(c + y);
+            });
+        }
+        Jcur = J + P.w_u * su; lgcur = lg; thetacur = th;
+        return true;
+    }
+
+    // value of the terminal state of buffer b
+    IGT_HD void terminal_of(int b, TermVal<T> &t, bool want_deriv)
+    {
+        terminal_value(w.Z(b, P.N, IS), w.Z(b, P.N, IV), t, want_deriv);
+    }
+
+    // sweeps 1-3.  Sets done/status on convergence or failure.
+    IGT_HD void backward()
+    {
+        const int N = P.N, b = cur;
+        if (need_back == 2) {
+            // ---- sweep 1: sensitivities
+            for (int k = 0; k < N; k++) {
+                T z[NZ], u[2] = { w.U(b, k, 0), w.U(b, k, 1) }, zn[NZ], S[NZ][NSEED];
+                load_z(b, k, z);
+                rk4_step_sens(P, z, u, curv, zn, S);
+#pragma unroll
+                for (int i = 0; i < NZ; i++)
+#pragma unroll
+                    for (int j = 0; j < NSEED; j++) w.Sens(k, i, j) = S[i][j];
+            }
+            // ---- sweep 2: adjoint + residuals
+            T lam[NA];
+            stat = T(0); rp = T(0); s_max = T(0); sy_min = T(1e30); sy_max = T(0);
+            for (int k = N; k >= 0; k--) {
+                T z[NZ], up[2], u[2] = { T(0), T(0) }, gw[NW];
+                load_z(b, k, z); load_up(b, k, up);
+                if (k < N) { u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1); }
+#pragma unroll
+                for (int i = 0; i < NW; i++) gw[i] = T(0);
+                int o = row_off(N, P.n_cinf, k);
+                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int i0, T g0, int i1, T g1, T, T, T) {
+                    T s = w.S(b, o + r), y = w.Y(b, o + r);
+                    gw[i0] += g0 * s;
+                    if (i1 >= 0) gw[i1] += g1 * s;
+                    rp = fmax(rp, fabs(c + y));
+                    s_max = fmax(s_max, s);
+                    T sy = s * y;
+                    sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
+                });
+                if (k == N) {
+#pragma unroll
+                    for (int i = 0; i < NA; i++) lam[i] = gw[i];
+                    lam[IEY] += T(2) * z[IEY]; lam[IEPSI] += T(2) * z[IEPSI];
+                    lam[IS] -= tcur.gs; lam[IV] -= tcur.gv;
+                } else {
+                    T S[NZ][NSEED], F[NA][NW];
+#pragma unroll
+                    for (int i = 0; i < NZ; i++)
+#pragma unroll
+                        for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
+                    build_F(P, S, F);
+                    T ln[NA];
+#pragma unroll
+                    for (int i = 0; i < NA; i++) ln[i] = lam[i];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        T gu = T(2) * P.w_u * u[j] + gw[NA + j];
+#pragma unroll
+                        for (int a = 0; a < NA; a++) if (fmask(a, NA + j)) gu += F[a][NA + j] * ln[a];
+                        stat = fmax(stat, fabs(gu));
+                    }
+#pragma unroll
+                    for (int i = 0; i < NA; i++) {
+                        T acc = gw[i];
+#pragma unroll
+                        for (int a = 0; a < NA; a++) if (fmask(a, i)) acc += F[a][i] * ln[a];
+                        lam[i] = acc;
+                    }
+                    lam[IEY] += T(2) * z[IEY]; lam[IEPSI] += T(2) * z[IEPSI];
+                }
+#pragma unroll
+                for (int i = 0; i < NZ; i++) w.Lam(k, i) = lam[i];
+            }
+            need_back = 1;
+        }
+        // ---- convergence test and barrier update (only with fresh residuals: ls == 0, reg change alone
+        //      does not alter them, so repeating the test is harmless)
+        if (stat <= P.tol * fmax(T(1), s_max) && rp <= P.tol_rp && sy_max <= P.tol_comp) {
+            status = 0; done = true;
+            return;
+        }
+        if (iters >= P.max_iter) { status = 1; done = true; return; }
+        while (mu > P.mu_floor &&
+               fmax(fmax(stat, rp), fmax(fabs(sy_max - mu), fabs(sy_min - mu))) <= P.kappa_eps * mu)
+            mu = fmax(P.mu_floor, fmin(P.kappa_mu * mu, pow(mu, P.theta_mu)));
+        phi = Jcur - tcur.V - mu * lgcur;
+        // ---- sweep 3: Riccati
+        for (;;) {
+            bool ok = true;
+            T Vx[NA], Vxx[45];
+            {
+#pragma unroll
+                for (int i = 0; i < 45; i++) Vxx[i] = T(0);
+#pragma unroll
+                for (int i = 0; i < NA; i++) Vx[i] = T(0);
+                T z[NZ], up[2], u[2] = { T(0), T(0) };
+                load_z(b, N, z); load_up(b, N, up);
+                Vx[IEY] = T(2) * z[IEY]; Vx[IEPSI] = T(2) * z[IEPSI];
+                Vx[IS] -= tcur.gs; Vx[IV] -= tcur.gv;
+                Vxx[sym9(IEY, IEY)] = T(2); Vxx[sym9(IEPSI, IEPSI)] = T(2);
+                Vxx[sym9(IS, IS)] -= tcur.Hss; Vxx[sym9(IS, IV)] -= tcur.Hsv; Vxx[sym9(IV, IV)] -= tcur.Hvv;
+                int o = row_off(N, P.n_cinf, N);
+                visit_rows(P, N, z, up, u, ox(N), oy(N), [&](int r, T c, int i0, T g0, int i1, T g1, T hxx, T hxy, T hyy) {
+                    T s = w.S(b, o + r), y = w.Y(b, o + r);
+                    T iy = T(1) / y, rhat = s * c + mu, sig = s * iy, gr = s + rhat * iy;
+                    Vx[i0] += g0 * gr;
+                    Vxx[sym9(i0, i0)] += sig * g0 * g0;
+                    if (i1 >= 0) {
+                        Vx[i1] += g1 * gr;
+                        Vxx[sym9(i1, i1)] += sig * g1 * g1;
+                        Vxx[sym9(i0, i1)] += sig * g0 * g1;
+                        Vxx[sym9(IX, IX)] += s * hxx; Vxx[sym9(IX, IY)] += s * hxy; Vxx[sym9(IY, IY)] += s * hyy;
+                    }
+                });
+            }
+            for (int k = N - 1; k >= 0; k--) {
+                T z[NZ], up[2], u[2] = { w.U(b, k, 0), w.U(b, k, 1) };
+                load_z(b, k, z); load_up(b, k, up);
+                T S[NZ][NSEED], F[NA][NW];
+#pragma unroll
+                for (int i = 0; i < NZ; i++)
+#pragma unroll
+                    for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
+                build_F(P, S, F);
+                T g[NW], H[66];
+                // g = F' Vx,  H = F' Vxx F   (structural zeros skipped at compile time)
+                T VF[NA][NW];
+#pragma unroll
+                for (int a = 0; a < NA; a++)
+#pragma unroll
+                    for (int j = 0; j < NW; j++) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int c = 0; c < NA; c++) if (fmask(c, j)) acc += Vxx[sym9(a, c)] * F[c][j];
+                        VF[a][j] = acc;
+                    }
+#pragma unroll
+                for (int i = 0; i < NW; i++) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int a = 0; a < NA; a++) if (fmask(a, i)) acc += F[a][i] * Vx[a];
+                    g[i] = acc;
+#pragma unroll
+                    for (int j = i; j < NW; j++) {
+                        T hh = T(0);
+#pragma unroll
+                        for (int a = 0; a < NA; a++) if (fmask(a, i)) hh += F[a][i] * VF[a][j];
+                        H[sym11(i, j)] = hh;
+                    }
+                }
+                // stage cost (mpc.py:359-364)
+                g[IEY] += T(2) * z[IEY]; g[IEPSI] += T(2) * z[IEPSI];
+                g[IUA] += T(2) * P.w_u * u[0]; g[IUD] += T(2) * P.w_u * u[1];
+                H[sym11(IEY, IEY)] += T(2); H[sym11(IEPSI, IEPSI)] += T(2);
+                H[sym11(IUA, IUA)] += T(2) * P.w_u; H[sym11(IUD, IUD)] += T(2) * P.w_u;
+                if (P.second_order) {
+                    T ln[NZ];
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
+                    add_dyn_hessian(P, z, u[1], curv, ln, H);
+                }
+                int o = row_off(N, P.n_cinf, k);
+                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int i0, T g0, int i1, T g1, T hxx, T hxy, T hyy) {
+                    T s = w.S(b, o + r), y = w.Y(b, o + r);
+                    T iy = T(1) / y, rhat = s * c + mu, sig = s * iy, gr = s + rhat * iy;
+                    g[i0] += g0 * gr;
+                    H[sym11(i0, i0)] += sig * g0 * g0;
+                    if (i1 >= 0) {
+                        g[i1] += g1 * gr;
+                        H[sym11(i1, i1)] += sig * g1 * g1;
+                        H[sym11(i0, i1)] += sig * g0 * g1;
+                        H[sym11(IX, IX)] += s * hxx; H[sym11(IX, IY)] += s * hxy; H[sym11(IY, IY)] += s * hyy;
+                    }
+                });
+                T q00 = H[sym11(IUA, IUA)] + reg, q11 = H[sym11(IUD, IUD)] + reg, q01 = H[sym11(IUA, IUD)];
+                T det = q00 * q11 - q01 * q01;
+                if (!(q00 > T(0) && det > T(1e-12) * q00 * q11)) { ok = false; break; }
+                T idet = T(1) / det;
+                T i00 = q11 * idet, i11 = q00 * idet, i01 = -q01 * idet;
+                T k0 = -(i00 * g[IUA] + i01 * g[IUD]), k1 = -(i01 * g[IUA] + i11 * g[IUD]);
+                T K0[NA], K1[NA];
+#pragma unroll
+                for (int j = 0; j < NA; j++) {
+                    T ha = H[sym11(j, IUA)], hd = H[sym11(j, IUD)];
+                    K0[j] = -(i00 * ha + i01 * hd);
+                    K1[j] = -(i01 * ha + i11 * hd);
+                    w.KK(k, 0, j) = K0[j]; w.KK(k, 1, j) = K1[j];
+                }
+                w.ku(k, 0) = k0; w.ku(k, 1) = k1;
+                T haa = H[sym11(IUA, IUA)], had = H[sym11(IUA, IUD)], hdd = H[sym11(IUD, IUD)];
+                T qk0 = haa * k0 + had * k1, qk1 = had * k0 + hdd * k1;
+#pragma unroll
+                for (int i = 0; i < NA; i++)
+                    Vx[i] = g[i] + K0[i] * (g[IUA] + qk0) + K1[i] * (g[IUD] + qk1) + H[sym11(i, IUA)] * k0 + H[sym11(i, IUD)] * k1;
+#pragma unroll
+                for (int i = 0; i < NA; i++)
+#pragma unroll
+                    for (int j = i; j < NA; j++) {
+                        T QK0j = haa * K0[j] + had * K1[j], QK1j = had * K0[j] + hdd * K1[j];
+                        Vxx[sym9(i, j)] = H[sym11(i, j)] + K0[i] * QK0j + K1[i] * QK1j
+                                          + K0[i] * H[sym11(j, IUA)] + K1[i] * H[sym11(j, IUD)]
+                                          + H[sym11(i, IUA)] * K0[j] + H[sym11(i, IUD)] * K1[j];
+                    }
+            }
+            if (ok) break;
+            reg = fmax(reg * P.reg_up, P.reg_min);
+            if (reg > P.reg_max) { status = 3; done = true; return; }
+        }
+        need_back = 0;
+        alpha = T(1);
+        ls = 0;
+    }
+
+    // one closed-loop forward pass with step alpha from buffer cur into buffer 1-cur
+    IGT_HD void forward_trial()
+    {
+        const int N = P.N, b = cur, nb = 1 - cur;
+        const T tau = fmax(P.tau_min, T(1) - mu);
+        T zn[NZ], upn[2] = { uprev[0], uprev[1] };
+        T J = T(0), su = T(0), lg = T(0), th = T(0);
+        bool fail = false;
+#pragma unroll
+        for (int i = 0; i < NZ; i++) { zn[i] = x0[i]; w.Z(nb, 0, i) = zn[i]; }
+        for (int k = 0; k <= N; k++) {
+            T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
+            load_z(b, k, z); load_up(b, k, up);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) dw[i] = zn[i] - z[i];
+            dw[IPA] = upn[0] - up[0]; dw[IPD] = upn[1] - up[1];
+            dw[IUA] = T(0); dw[IUD] = T(0);
+            if (k < N) {
+                u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1);
+                T d0 = alpha * w.ku(k, 0), d1 = alpha * w.ku(k, 1);
+#pragma unroll
+                for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dw[j]; d1 += w.KK(k, 1, j) * dw[j]; }
+                dw[IUA] = d0; dw[IUD] = d1;
+            }
+            int o = row_off(N, P.n_cinf, k);
+            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int i0, T g0, int i1, T g1, T, T, T) {
+                T s = w.S(b, o + r), y = w.Y(b, o + r);
+                T dc = g0 * dw[i0] + (i1 >= 0 ? g1 * dw[i1] : T(0));
+                T yn = y - alpha * (c + y) - dc;
+                T sn = s + (alpha * (s * c + mu) + s * dc) / y;
+                if (yn < (T(1) - tau) * y || sn < (T(1) - tau) * s) fail = true;
+                w.Y(nb, o + r) = yn; w.S(nb, o + r) = sn;
+            });
+            if (fail) break;
+            T un[2] = { u[0] + dw[IUA], u[1] + dw[IUD] };
+            // rows at the new point: infeasibility and barrier terms
+            visit_rows(P, k, zn, upn, un, ox(k), oy(k), [&](int r, T c, int, T, int, T, T, T, T) {
+                T yn = w.Y(nb, o + r);
+                th += fabs(c + yn);
+                lg += log(yn);
+            });
+            J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
+            if (k == N) break;
+            su += un[0] * un[0] + un[1] * un[1];
+            w.U(nb, k, 0) = un[0]; w.U(nb, k, 1) = un[1];
+            T zz[NZ];
+            rk4_step(P, zn, un, curv, zz);
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) { zn[i] = zz[i]; w.Z(nb, k + 1, i) = zz[i]; fin = fin && (zz[i] == zz[i]) && fabs(zz[i]) < T(1e15); }
+            if (!fin) { fail = true; break; }
+            upn[0] = un[0]; upn[1] = un[1];
+        }
+        trial_ok = !fail;
+        Jcand = J + P.w_u * su; lgcand = lg; thetacand = th;
+    }
+
+    // acceptance test (needs tcand of the candidate's terminal state when trial_ok)
+    IGT_HD void finish_trial()
+    {
+        bool accepted = false;
+        if (trial_ok) {
+            T phin = Jcand - tcand.V - mu * lgcand;
+            accepted = (phin == phin) && fabs(phin) < T(1e30) &&
+                       (phin < phi - P.eps_phi * fabs(phi) || thetacand < thetacur * (T(1) - P.gamma_theta) ||
+                        (thetacand <= P.theta_small && phin <= phi + P.eps_phi * fmax(T(1), fabs(phi))));
+        }
+        if (accepted) {
+            cur = 1 - cur;
+            Jcur = Jcand; lgcur = lgcand; thetacur = thetacand; tcur = tcand;
+            reg = reg > P.reg_min ? reg / P.reg_down : T(0);
+            need_back = 2;
+            iters++;
+        } else {
+            alpha *= T(0.5);
+            ls++;
+            if (ls >= P.n_alpha) {
+                reg = fmax(reg * P.reg_up, P.reg_min);
+                iters++;
+                if (reg > P.reg_max) { status = 4; done = true; }
+                need_back = 1;
+            }
+        }
+    }
+
+    // write the outputs of this problem (x, u, cost, max row violation in reference units)
+    IGT_HD void write_out(const ProbIO &io, long p)
+    {
+        const int N = P.N, b = cur;
+        if (status == 2) {
+            for (int i = 0; i < (N + 1) * NZ; i++) io.x[p * (N + 1) * NZ + i] = NAN;
+            for (int i = 0; i < N * 2; i++) io.u[p * N * 2 + i] = NAN;
+            io.cost[p] = NAN; io.viol[p] = INFINITY; io.status[p] = 2; io.iters[p] = 0;
+            return;
+        }
+        T m = T(0);
+        for (int k = 0; k <= N; k++) {
+            T z[NZ], up[2];
+            load_z(b, k, z); load_up(b, k, up);
+            for (int i = 0; i < NZ; i++) io.x[(p * (N + 1) + k) * NZ + i] = double(z[i]);
+            m = fmax(m, fabs(z[IEY]) - P.ey_lim);
+            if (k >= 1) {
+                T dx = z[IX] - ox(k), dy = z[IY] - oy(k);
+                m = fmax(m, P.d_min * P.d_min - dx * dx - dy * dy);
+            }
+            if (k < N) {
+                T u[2] = { w.U(b, k, 0), w.U(b, k, 1) };
+                io.u[(p * N + k) * 2] = double(u[0]); io.u[(p * N + k) * 2 + 1] = double(u[1]);
+                m = fmax(m, fmax(P.v_min - z[IV], z[IV] - P.v_max));
+                m = fmax(m, fmax(P.a_min - u[0], u[0] - P.a_max));
+                m = fmax(m, fabs(u[1]) - P.df_max);
+                m = fmax(m, fabs(u[0] - up[0]) - P.da_max);
+                m = fmax(m, fabs(u[1] - up[1]) - P.ddf_max);
+                if (k == N - 1)
+                    for (int q = 0; q < P.n_cinf; q++)
+                        m = fmax(m, P.cinf_A[q][0] * z[IV] + P.cinf_A[q][1] * u[0] - P.cinf_b[q]);
+            }
+        }
+        io.cost[p] = double(Jcur - tcur.V);
+        io.viol[p] = double(m);
+        io.status[p] = status;
+        io.iters[p] = iters;
+    }
+};
+
+// Whole solve of problem p, one thread.  (kernels.cu wraps this; tests/hostsim calls it on the CPU.)
+template <typename T>
+IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, long stride, long p,
+                          T *mlp_scratch, int mlp_width)
+{
+    Solver<T> sv(P);
+    sv.w.base = ws_base; sv.w.stride = stride; sv.w.p = p;
+    sv.w.L.init(P.N, P.n_cinf);
+    sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
+    if (sv.init(io, p, io.ctx != nullptr, io.u_init != nullptr)) {
+        sv.terminal_of(sv.cur, sv.tcur, true);
+        while (!sv.done) {
+            if (sv.need_back) sv.backward();
+            if (sv.done) break;
+            sv.forward_trial();
+            if (sv.trial_ok) sv.terminal_of(1 - sv.cur, sv.tcand, true);
+            sv.finish_trial();
+        }
+    }
+    sv.write_out(io, p);
+}
+
+}  // namespace igt

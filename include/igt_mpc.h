@@ -1,0 +1,135 @@
+/* igt_mpc.h -- C ABI of the B200-native batched MPC solver (libigtmpc.so).
+ *
+ * Drop-in boundary for the solver behind the reference's MPC_Planner
+ * (reference mpc.py:21-406).  The reference has no FFI of its own -- mpc.py talks to CasADi's
+ * Python API -- so each entry point below names the reference call site(s) it replaces.  The
+ * Python host (igt_mpc_int_b200/planner.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer would add to the reference's mpc.py.
+ *
+ * Conventions: plain pointers and sizes only; every array is contiguous, batch-major
+ * ("problem b" first).  `*_dev` entry points take DEVICE pointers and enqueue work on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) without synchronising;
+ * `*_host` entry points take HOST pointers, copy in, run, copy out and synchronise.
+ * Every function returns 0 on success or a negative IGT_E* code; igt_last_error() gives text.
+ * No C++ exception crosses this boundary.
+ *
+ * Layouts (reference mpc.py:163-164):  state z = [x, y, s, ey, epsi, v, psi], input u = [a, df].
+ */
+#ifndef IGT_MPC_H
+#define IGT_MPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGT_MAX_CINF 128
+#define IGT_MAX_MLP_LAYERS 5
+
+#define IGT_OK 0
+#define IGT_EINVAL (-1)   /* bad argument (NULL, size, unsupported horizon ...) */
+#define IGT_ECUDA (-2)    /* CUDA runtime error */
+#define IGT_ENOMLP (-3)   /* gt_mpc solve requested before igt_set_mlp */
+
+/* per-problem status written by igt_solve_* (reference mpc.py:402-406 maps any failure to
+ * (None, None, False); the Python host maps status != 0 the same way) */
+#define IGT_STATUS_CONVERGED 0
+#define IGT_STATUS_MAXITER 1
+#define IGT_STATUS_X0_INFEASIBLE 2   /* x0 violates rows that involve x0 only (mpc.py:298-299,316-317 at k=0) */
+#define IGT_STATUS_REG_LIMIT 3
+#define IGT_STATUS_LINESEARCH 4
+
+#define IGT_PREC_F32 0
+#define IGT_PREC_F64 1
+
+typedef struct igt_handle igt_handle;
+
+typedef struct {
+    /* ---- problem constants: effective values of mpc.py:47-62, mpc.yaml, fourwayint.yaml ---- */
+    int N;            /* horizon, mpc.yaml:6 (10, 20 or 40 ... any 2 <= N <= 64) */
+    int n_rk;         /* RK4 sub-steps per MPC step, evaluate.py:109 */
+    double dt;        /* mpc.yaml:7 */
+    double l_r, l_f;  /* mpc.py:50-51 */
+    double v_min, v_max, a_min, a_max, df_max, ey_lim;   /* mpc.py:56-61 */
+    double da_max, ddf_max;   /* dt*jerk_limit, dt*steering_rate_limit: mpc.py:54-55, :301-312 */
+    double d_min;     /* 2*ca_radius, mpc.py:45 */
+    double w_u;       /* 0.05, mpc.py:362 */
+    int n_cinf;       /* rows of the terminal invariant set, mpc.py:88-104,:177-180 */
+    double cinf_A[IGT_MAX_CINF][2];
+    double cinf_b[IGT_MAX_CINF];
+    /* ---- solver options (stand in for the IPOPT options of mpc.py:130-146) ---- */
+    double tol;        /* stationarity: |grad_u Lagrangian|_inf <= tol * max(1, |mult|_inf) */
+    double tol_rp;     /* primal residual |c + slack|_inf (bounds the row violation) */
+    double tol_comp;   /* complementarity max(mult*slack) */
+    double mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min;
+    double reg_min, reg_up, reg_down, reg_max;
+    double eps_phi, gamma_theta, theta_small;
+    int max_iter;      /* mpc.py:137 uses 100*N for IPOPT */
+    int n_alpha;       /* step halvings per line search */
+    int second_order;  /* add the dt*Hess(lambda.f) curvature term to the Riccati pass */
+    int precision;     /* IGT_PREC_F32 / IGT_PREC_F64: arithmetic of the solver kernels */
+} igt_params;
+
+/* Fill `p` with the reference's effective constants (N=40, dt=0.1, n_rk=4, limits of
+ * mpc.py:47-62) and default solver options for `precision`.  The C_inf table is left empty
+ * (n_cinf = 0): the host computes it (igt_mpc_int_b200/terminal_set.py restates
+ * common/utils.py:588-627) and stores it here before igt_create. */
+int igt_default_params(igt_params *p, int precision);
+
+/* Replaces MPC_Planner.__init__ (mpc.py:21-160): builds the immutable solver object. */
+int igt_create(const igt_params *p, igt_handle **out);
+void igt_destroy(igt_handle *h);
+const char *igt_last_error(const igt_handle *h);   /* h may be NULL: last create error */
+
+/* Replaces mpc.py:105-127 (loading the value network and its normalisation).
+ * n_layers linear layers with tanh between them (model.py:14-51); W[l] is row-major
+ * [dims[l+1], dims[l]], dims[0] == 6, dims[n_layers] == 1.  Wn = 6x6 whitening matrix
+ * (mpc.py:116), mu_f[6] feature mean, sigma_t / mu_t target scaling (mpc.py:117-118). */
+int igt_set_mlp(igt_handle *h, int n_layers, const int *dims, const double *const *W,
+                const double *const *b, const double *Wn, const double *mu_f, double sigma_t,
+                double mu_t);
+
+/* Replaces KinematicBicycleModelFrenet.__call__ (common/kinematic_bicycle_model_frenet.py:
+ * 69-185; model 0) and KinematicBicycleModel.__call__ (common/kinematic_bicycle_model.py:
+ * 15-50; model 1) rolled over the horizon, plus the Jacobians CasADi derives by AD.
+ * fp32 device arrays.  model 0: z0[B,7], u[B,N,2], curv[B,3] = (b0, b1, Kval) of the pw_const
+ * curvature (mpc.py:183-200), z[B,N+1,7], A[B,N,7,7], Bm[B,N,7,2].
+ * model 1: z0[B,4] = (x, y, psi, v), z[B,N+1,4], A[B,N,4,4], Bm[B,N,4,2], curv ignored.
+ * A and Bm may both be NULL. */
+int igt_rollout_dev(igt_handle *h, int B, const float *z0, const float *u, const float *curv,
+                    float *z, float *A, float *Bm, int model, void *stream);
+int igt_rollout_host(igt_handle *h, int B, const float *z0, const float *u, const float *curv,
+                     float *z, float *A, float *Bm, int model);
+
+/* Cost (mpc.py:356-373) and the largest inequality-row value, rows exactly as written in
+ * mpc.py:177-180,:223-226,:296-321 (collision in squared-distance units), of given controls.
+ * The state trajectory is re-rolled on the device.  fp64 arrays: x0[B,7], u_prev[B,2],
+ * curv[B,3], obs_xy[B,N+1,2], nn_ctx[B,4] = (s_tv, v_tv, e_tv, e_ego) or NULL ('mpc' cost),
+ * u[B,N,2] -> cost[B], viol[B], z[B,N+1,7] (z may be NULL). */
+int igt_eval_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                  const double *obs_xy, const double *nn_ctx, const double *u, double *cost,
+                  double *viol, double *z);
+
+/* Replaces MPC_Planner.update_initial_condition / update_predictions / solve
+ * (mpc.py:280-294, :241-278, :383-406) for a batch of independent problems.
+ * In : x0[B,7]; u_prev[B,2]; curv[B,3]; obs_xy[B,N+1,2] (row 0 unused, mpc.py:224);
+ *      nn_ctx[B,4] or NULL -- non-NULL selects the gt_mpc terminal cost (mpc.py:367-369);
+ *      u_init[B,N,2] or NULL -- warm start (mpc.py:386-389); NULL = cold-start rule.
+ * Out: x[B,N+1,7], u[B,N,2], cost[B], viol[B] (max inequality row, reference units),
+ *      status[B] (IGT_STATUS_*), iters[B].  All fp64 / int32. */
+int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                  const double *obs_xy, const double *nn_ctx, const double *u_init, double *x,
+                  double *u, double *cost, double *viol, int *status, int *iters, void *stream);
+int igt_solve_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                   const double *obs_xy, const double *nn_ctx, const double *u_init, double *x,
+                   double *u, double *cost, double *viol, int *status, int *iters);
+
+/* Number of kernels this library has launched on `h` so far (bench.py's gpu_launches). */
+long long igt_launch_count(const igt_handle *h);
+
+/* Library build info: returns e.g. "igtmpc 0.1 sm_100a". */
+const char *igt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGT_MPC_H */

@@ -1,0 +1,161 @@
+"""CUDA solver through the C ABI vs the fp64 oracle (same seeded problems)."""
+import numpy as np
+import pytest
+
+from tests.util import relerr
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = dict(tol=1e-6, tol_rp=1e-8, tol_comp=1e-7, mu_floor=1e-8, max_iter=300)
+
+
+def _solver(N, **kw):
+    from igt_mpc_int_b200.planner import BatchSolver
+    return BatchSolver(N=N, **kw)
+
+
+@pytest.mark.parametrize("N,B", [(40, 512), (20, 128), (10, 128)])
+def test_solver_matches_oracle_tight(oracle_params, N, B):
+    """Same algorithm, same options, fp64 on both sides: identical outcomes per problem."""
+    from oracle import c_oracle
+    from igt_mpc_int_b200 import scenarios as S
+    pb = S.mid_episode(B, N=N)
+    s = _solver(N, **TIGHT)
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    o = c_oracle.COracle(oracle_params[N]).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    assert np.mean(r["status"] == o["status"]) > 0.99
+    ok = (o["status"] == 0) & (r["status"] == 0)
+    assert ok.sum() > 0.8 * B
+    assert np.max(relerr(r["cost"][ok], o["cost"][ok])) < 1e-4          # denominator max(|J|, 1)
+    assert np.max(np.abs(r["u"][ok] - o["U"][ok])) < 1e-3
+    assert np.max(r["viol"][ok]) <= 1e-6
+    assert np.max(relerr(r["x"][ok], o["Z"][ok])) < 1e-6
+    s.close()
+
+
+def test_solver_default_options_parity(oracle_params):
+    """Product defaults (what bench.py runs) against the tight oracle: north-star tolerances."""
+    from oracle import c_oracle
+    from igt_mpc_int_b200 import scenarios as S
+    B, N = 1024, 40
+    for gen, seed in ((S.mid_episode, 123), (S.episode_start, 2026)):
+        pb = gen(B, N=N, seed=seed)
+        s = _solver(N)
+        r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+        o = c_oracle.COracle(oracle_params[N]).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
+        ok = (o["status"] == 0) & (r["status"] == 0)
+        assert ok.sum() > 0.85 * B
+        assert np.mean((r["status"] == 0) == (o["status"] == 0)) > 0.98
+        assert np.max(relerr(r["cost"][ok], o["cost"][ok])) < 1e-4
+        assert np.max(np.abs(r["u"][ok] - o["U"][ok])) < 1e-3
+        assert np.max(r["viol"][ok]) <= 1e-6
+        # the device-side evaluation of the returned controls agrees with the oracle's
+        ev = s.evaluate(pb.x0[ok], pb.u_prev[ok], pb.curv[ok], pb.obs[ok], r["u"][ok])
+        oc, ov = c_oracle.COracle(oracle_params[N]).eval(pb.x0[ok], pb.u_prev[ok], pb.curv[ok], pb.obs[ok],
+                                                          ev["x"], r["u"][ok])
+        assert np.max(relerr(ev["cost"], oc)) < 1e-12 and np.max(np.abs(ev["viol"] - ov)) < 1e-12
+        s.close()
+
+
+def test_solver_edge_cases():
+    from igt_mpc_int_b200 import scenarios as S
+    from igt_mpc_int_b200 import _lib
+    s = _solver(40)
+    out = s.solve_batch(np.zeros((0, 7)), np.zeros((0, 2)), np.zeros((0, 3)), np.zeros((0, 41, 2)))
+    assert out["x"].shape == (0, 41, 7)
+    pb = S.mid_episode(8, N=40, seed=5)
+    x0 = pb.x0.copy(); x0[0, 5] = 5.5; x0[1, 3] = 0.3
+    r = s.solve_batch(x0, pb.u_prev, pb.curv, pb.obs)
+    assert r["status"][0] == 2 and r["status"][1] == 2 and np.isnan(r["cost"][0])
+    # ragged batch size (not a multiple of the block size) and warm start
+    pb = S.mid_episode(104, N=40, seed=9).slice(0, 97)
+    cold = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    ok = cold["status"] == 0
+    warm = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, u_init=np.nan_to_num(cold["u"]))
+    assert np.all(warm["status"][ok] == 0)
+    assert np.max(relerr(warm["cost"][ok], cold["cost"][ok])) < 1e-4
+    assert np.median(warm["iters"][ok]) < np.median(cold["iters"][ok])
+    with pytest.raises(_lib.IgtError):
+        s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, nn_ctx=pb.nn_ctx)      # no MLP set
+    with pytest.raises(ValueError):
+        s.solve_batch(pb.x0, pb.u_prev[:, :1], pb.curv, pb.obs)
+    s.close()
+
+
+def test_solver_device_pointer_path_matches_host_path():
+    import torch
+    from igt_mpc_int_b200 import scenarios as S
+    pb = S.mid_episode(256, N=40, seed=17)
+    s = _solver(40)
+    host = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dev = s.solve_batch_device(t(pb.x0), t(pb.u_prev), t(pb.curv), t(pb.obs))
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["status"].cpu().numpy(), host["status"])
+    assert np.array_equal(dev["u"].cpu().numpy(), host["u"], equal_nan=True)
+    assert s.launches >= 2
+    s.close()
+
+
+def test_fp32_solver_quality(oracle_params):
+    """The fp32 arithmetic option: reported, looser (it is not the parity path)."""
+    from oracle import c_oracle
+    from igt_mpc_int_b200 import scenarios as S
+    pb = S.mid_episode(512, N=40, seed=3)
+    s = _solver(40, precision="f32")
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    o = c_oracle.COracle(oracle_params[40]).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    ok = (o["status"] == 0) & (r["status"] == 0)
+    assert ok.sum() > 0.8 * len(pb)
+    assert np.median(relerr(r["cost"][ok], o["cost"][ok])) < 1e-3
+    assert np.max(r["viol"][ok]) <= 1e-3
+    s.close()
+
+
+def test_planner_protocol_matches_reference_interface(oracle_params):
+    """MPC_Planner mirror: constructor keywords, three-method protocol, return shapes
+    (mpc.py:21-37, :241-294, :383-406)."""
+    from igt_mpc_int_b200.planner import MPC_Planner
+    from igt_mpc_int_b200 import geometry as G
+    from oracle import c_oracle
+
+    class Bag:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    N = 40
+    routes = ['12', '31']
+    refs = []
+    for r in routes:
+        b0, b1, kv = G.curvature_params(r)
+        K = np.zeros(151)
+        if kv != 0.0:
+            K[40:70] = kv
+        refs.append({'K': K})
+    agents = []
+    for r, s0 in zip(routes, (5.0, 3.0)):
+        x, y, th = G.frenet2global(s0, r)
+        agents.append({'type': 'CAV', 'state': Bag(x=x, y=y, heading=th, v=0.0, s=s0, ey=0.0, epsi=0.0)})
+    pl = MPC_Planner(N=N, dt=0.1, ca_radius=2.8, agents=agents, routes=routes, ref=refs, goals=None,
+                     road_dim=(11.4, 50.0), ds_right=8.6, index=0, num_rk4_steps=4)
+    pl.update_initial_condition(agents[0], Bag(a=0.1, df=0.0))
+    preds = []
+    for r, ag in zip(routes, agents):
+        fc = G.constant_acceleration_forecast(ag['state'].s, 0.0, 0.1, r, N)
+        preds.append([Bag(x=p[0], y=p[1], s=p[2], v=p[3], heading=0.0, ey=0.0, epsi=0.0) for p in fc])
+    pl.update_predictions(preds, raw_preds=preds)
+    x, u, ok = pl.solve()
+    assert ok and x.shape == (7, N + 1) and u.shape == (2, N) and x.dtype == np.float64
+    assert pl.solve_time > 0 and pl.sol.stats()["success"] and pl.x_sol_prev is x
+    # same problem through the oracle
+    obs = np.array([[p.x, p.y] for p in preds[1]])[None]
+    o = c_oracle.COracle(oracle_params[N]).solve(pl._x0, pl._uprev, pl.curv, obs)
+    assert o["status"][0] == 0 and abs(o["cost"][0] + 0.0) < 50
+    assert np.max(np.abs(u.T - o["U"][0])) < 1e-3
+    # warm start with the previous solution, like evaluate.py:478-482
+    x2, u2, ok2 = pl.solve(x_sol_prev=x, u_sol_prev=u)
+    assert ok2 and np.max(np.abs(u2 - u)) < 1e-3
+    # infeasible initial state -> (None, None, False), never raises (mpc.py:402-406)
+    agents[0]['state'].v = 9.0
+    pl.update_initial_condition(agents[0], Bag(a=0.1, df=0.0))
+    assert pl.solve() == (None, None, False)
