@@ -21,6 +21,11 @@
 
 using namespace igt;
 
+// resident solver threads per SM (255 registers/thread -> 4 blocks of 64)
+#ifndef SLOTS_PER_SM
+#define SLOTS_PER_SM 256
+#endif
+
 // ------------------------------------------------------------------ device constants ----
 __constant__ DevParams<float> c_Pf;
 __constant__ DevParams<double> c_Pd;
@@ -30,13 +35,26 @@ template <> struct ConstP<float> { static __device__ __forceinline__ const DevPa
 template <> struct ConstP<double> { static __device__ __forceinline__ const DevParams<double> &get() { return c_Pd; } };
 
 // ------------------------------------------------------------------ kernels -------------
+// cold-start guess: best of five tracking-controller rollouts per problem -> guess[B][N][2]
 template <typename T>
-__global__ void __launch_bounds__(64) solve_kernel(ProbIO io, T *ws, long B, T *mlp_scratch, int mlp_width)
+__global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *guess)
 {
     long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     const DevParams<T> &P = ConstP<T>::get();
-    solve_problem<T>(P, io, ws, B, p, mlp_scratch ? mlp_scratch + p * 12 * (long)mlp_width : nullptr, mlp_width);
+    Solver<T> sv(P);
+    sv.compute_guess(io, p, guess + p * P.N * 2);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) solve_kernel(ProbIO io, T *ws, long n_slots, long B,
+                                                   unsigned long long *counter, const double *guess,
+                                                   T *mlp_scratch, int mlp_width)
+{
+    long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;   // grid is sized to n_slots exactly
+    const DevParams<T> &P = ConstP<T>::get();
+    solve_persistent<T>(P, io, ws, slot, B, counter, guess,
+                        mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width);
 }
 
 // fp32 rollout with Kahan-compensated accumulation of the RK4 increments (x, y, s reach ~50 m
@@ -179,6 +197,8 @@ struct igt_handle {
     void *ws = nullptr; size_t ws_bytes = 0;
     void *mlp_scratch = nullptr; size_t mlp_scratch_bytes = 0;
     void *stage = nullptr; size_t stage_bytes = 0;     // device staging for *_host calls
+    void *guess = nullptr; size_t guess_bytes = 0;     // cold-start controls [B][N][2] + the work counter
+    int n_sm = 0;
     long long launches = 0;
     std::string err;
     int device = 0;
@@ -229,6 +249,8 @@ int igt_create(const igt_params *p, igt_handle **out)
         delete h;
         return IGT_ECUDA;
     }
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->n_sm <= 0) h->n_sm = 148;
     *out = h;
     return IGT_OK;
 }
@@ -240,6 +262,7 @@ void igt_destroy(igt_handle *h)
     if (h->ws) cudaFree(h->ws);
     if (h->mlp_scratch) cudaFree(h->mlp_scratch);
     if (h->stage) cudaFree(h->stage);
+    if (h->guess) cudaFree(h->guess);
     delete h;
 }
 
@@ -347,18 +370,36 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     const bool f64 = h->prm.precision == IGT_PREC_F64;
     WsLayout L; L.init(h->prm.N, h->prm.n_cinf);
     size_t esz = f64 ? 8 : 4;
-    int rc = grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * B * esz);
+    // persistent lanes: at most SLOTS_PER_SM threads per SM, never more than problems
+    const int bs = 64;
+    long max_slots = (long)h->n_sm * SLOTS_PER_SM;
+    long n_slots = ((B + bs - 1) / bs) * (long)bs;
+    if (n_slots > max_slots) n_slots = max_slots;
+    int rc = grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * n_slots * esz);
     if (rc) return rc;
     if (nn_ctx) {
-        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * B * esz);
+        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * n_slots * esz);
         if (rc) return rc;
     }
+    rc = grow(h, &h->guess, &h->guess_bytes, 256 + (size_t)B * h->prm.N * 2 * sizeof(double));
+    if (rc) return rc;
+    unsigned long long *counter = (unsigned long long *)h->guess;
+    double *guess = (double *)((char *)h->guess + 256);
     rc = upload_params(h, st, !f64, f64);
     if (rc) return rc;
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     ProbIO io = { x0, u_prev, curv, obs_xy, nn_ctx, u_init, x, u, cost, viol, status, iters };
-    int bs = 64, gs = (B + bs - 1) / bs;
-    if (f64) solve_kernel<double><<<gs, bs, 0, st>>>(io, (double *)h->ws, B, nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width);
-    else solve_kernel<float><<<gs, bs, 0, st>>>(io, (float *)h->ws, B, nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width);
+    if (!u_init) {
+        int gbs = 128, ggs = (B + gbs - 1) / gbs;
+        if (f64) guess_kernel<double><<<ggs, gbs, 0, st>>>(io, B, guess);
+        else guess_kernel<float><<<ggs, gbs, 0, st>>>(io, B, guess);
+        h->launches++;
+    }
+    int gs = (int)(n_slots / bs);
+    if (f64) solve_kernel<double><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, counter, guess,
+                                                     nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width);
+    else solve_kernel<float><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, counter, guess,
+                                                nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width);
     h->launches++;
     CK(cudaGetLastError());
     return IGT_OK;

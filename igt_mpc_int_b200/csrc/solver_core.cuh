@@ -44,7 +44,7 @@ struct DevParams {
     int dims[MAX_MLP_LAYERS + 1];
     T dt, h, l_r, lsum, inv_lr, rho;
     T v_min, v_max, a_min, a_max, df_max, ey_lim, da_max, ddf_max, d_min, w_u;
-    T tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min;
+    T tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min, mu0_warm, y_init_min_warm, alpha_safety;
     T reg_min, reg_up, reg_down, reg_max, eps_phi, gamma_theta, theta_small;
     T cinf_A[MAX_CINF][2], cinf_b[MAX_CINF];
     T Wn[36], mu_f[6], sigma_t, mu_t;
@@ -84,13 +84,16 @@ struct WsLayout {
     }
 };
 
+// Workspace addressing: slots are grouped by warp; element e of slot q lives at
+//   base[(q / 32) * total * 32 + e * 32 + (q % 32)]
+// so the 32 lanes of a warp touch 32 consecutive words for every element, and every element
+// offset that is a compile-time constant folds into the load/store immediate.
 template <typename T>
 struct Ws {
-    T *base;
-    long stride;    // number of problems in the launch
-    long p;         // this problem
+    T *wb;          // base + (slot / 32) * total * 32 + slot % 32
     WsLayout L;
-    IGT_HD T &at(int e) const { return base[(long)e * stride + p]; }
+    IGT_HD void bind(T *base, long slot) { wb = base + (slot / 32) * (long)L.total * 32 + (slot % 32); }
+    IGT_HD T &at(int e) const { return wb[e * 32]; }
     IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ[b] + k * NZ + i); }
     IGT_HD T &U(int b, int k, int i) const { return at(L.oU[b] + k * 2 + i); }
     IGT_HD T &Y(int b, int r) const { return at(L.oY[b] + r); }
@@ -109,6 +112,9 @@ struct ProbIO {
 };
 
 // ------------------------------------------------------------------ dynamics -----------
+IGT_HD void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
+IGT_HD void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+
 template <typename T>
 struct Slip { T beta, dbeta, sb, cb; };
 
@@ -119,8 +125,7 @@ IGT_HD Slip<T> slip_of(const DevParams<T> &P, T df)
     T t = tan(df);
     r.beta = atan(P.rho * t);
     r.dbeta = P.rho * (T(1) + t * t) / (T(1) + P.rho * P.rho * t * t);
-    r.sb = sin(r.beta);
-    r.cb = cos(r.beta);
+    sincos_t(r.beta, &r.sb, &r.cb);
     return r;
 }
 
@@ -139,8 +144,9 @@ IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const
 {   // kinematic_bicycle_model_frenet.py:71-91
     T ey = z[IEY], epsi = z[IEPSI], v = z[IV], psi = z[IPSI];
     T K = curvature(z[IS], curv[0], curv[1], curv[2]);
-    T c1 = cos(sl.beta + epsi), s1 = sin(sl.beta + epsi);
-    T cp = cos(psi + sl.beta), sp = sin(psi + sl.beta);
+    T c1, s1, cp, sp;
+    sincos_t(sl.beta + epsi, &s1, &c1);
+    sincos_t(psi + sl.beta, &sp, &cp);
     T iden = T(1) / (T(1) - K * ey);
     T sdot = v * c1 * iden;
     T yaw = v * sl.sb * P.inv_lr;
@@ -168,29 +174,31 @@ IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const
 }
 
 // one MPC step, values only.  k4 evaluates xdot, ydot at psi + h/2*k3[psi]
-// (kinematic_bicycle_model_frenet.py:111) -- reproduced on purpose.
+// (kinematic_bicycle_model_frenet.py:111) -- reproduced on purpose.  The four stages run as a
+// loop (one copy of the right-hand side in the instruction stream, not sixteen).
 template <typename T>
-IGT_HD void rk4_step(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn)
+IGT_HDN void rk4_step(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn)
 {
     const T h = P.h;
     Slip<T> sl = slip_of(P, u[1]);
-    T z[NZ], zs[NZ], k1[NZ], k2[NZ], k3[NZ], k4[NZ];
+    T z[NZ], zs[NZ], k[NZ], kacc[NZ];
 #pragma unroll
     for (int i = 0; i < NZ; i++) z[i] = z0[i];
+#pragma unroll 1
     for (int it = 0; it < P.n_rk; it++) {
-        rhs<T, false>(P, z, u[0], sl, curv, k1, nullptr);
 #pragma unroll
-        for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * T(0.5) * k1[i];
-        rhs<T, false>(P, zs, u[0], sl, curv, k2, nullptr);
+        for (int i = 0; i < NZ; i++) { zs[i] = z[i]; kacc[i] = T(0); }
+#pragma unroll 1
+        for (int st = 0; st < 4; st++) {
+            rhs<T, false>(P, zs, u[0], sl, curv, k, nullptr);
+            const T wgt = (st == 0 || st == 3) ? T(1) : T(2);
+            const T cf = (st == 2) ? T(1) : T(0.5);
 #pragma unroll
-        for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * T(0.5) * k2[i];
-        rhs<T, false>(P, zs, u[0], sl, curv, k3, nullptr);
+            for (int i = 0; i < NZ; i++) { kacc[i] += wgt * k[i]; zs[i] = z[i] + h * cf * k[i]; }
+            if (st == 2) zs[IPSI] = z[IPSI] + h * T(0.5) * k[IPSI];
+        }
 #pragma unroll
-        for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * k3[i];
-        zs[IPSI] = z[IPSI] + h * T(0.5) * k3[IPSI];
-        rhs<T, false>(P, zs, u[0], sl, curv, k4, nullptr);
-#pragma unroll
-        for (int i = 0; i < NZ; i++) z[i] += h / T(6) * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+        for (int i = 0; i < NZ; i++) z[i] += h / T(6) * kacc[i];
     }
 #pragma unroll
     for (int i = 0; i < NZ; i++) zn[i] = z[i];
@@ -219,7 +227,7 @@ IGT_HD void rhs_tangent(const RhsJac<T> &J, const T (*Ts)[NSEED], T (*dk)[NSEED]
 // one MPC step with sensitivities w.r.t. the 6 seeds (ey, epsi, v, psi, a, df): S[7][6].
 // dF/dx = e_x, dF/dy = e_y, dF/ds = e_s (dK/ds == 0) complete the Jacobian.
 template <typename T>
-IGT_HD void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn, T (*S)[NSEED])
+IGT_HDN void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn, T (*S)[NSEED])
 {
     const T h = P.h;
     Slip<T> sl = slip_of(P, u[1]);
@@ -233,46 +241,34 @@ IGT_HD void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u, const 
         for (int j = 0; j < NSEED; j++) S[i][j] = T(0);
     }
     S[IEY][0] = T(1); S[IEPSI][1] = T(1); S[IV][2] = T(1); S[IPSI][3] = T(1);
+#pragma unroll 1
     for (int it = 0; it < P.n_rk; it++) {
-        // k1
-        rhs<T, true>(P, z, u[0], sl, curv, k, &J);
-        rhs_tangent(J, S, dk);
 #pragma unroll
         for (int i = 0; i < NZ; i++) {
-            kacc[i] = k[i];
-            zs[i] = z[i] + h * T(0.5) * k[i];
+            zs[i] = z[i]; kacc[i] = T(0);
 #pragma unroll
-            for (int j = 0; j < NSEED; j++) { dacc[i][j] = dk[i][j]; Ts[i][j] = S[i][j] + h * T(0.5) * dk[i][j]; }
+            for (int j = 0; j < NSEED; j++) { Ts[i][j] = S[i][j]; dacc[i][j] = T(0); }
         }
-        // k2
-        rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
-        rhs_tangent(J, Ts, dk);
+#pragma unroll 1
+        for (int st = 0; st < 4; st++) {
+            rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
+            rhs_tangent(J, Ts, dk);
+            const T wgt = (st == 0 || st == 3) ? T(1) : T(2);
+            const T cf = (st == 2) ? T(1) : T(0.5);
 #pragma unroll
-        for (int i = 0; i < NZ; i++) {
-            kacc[i] += T(2) * k[i];
-            zs[i] = z[i] + h * T(0.5) * k[i];
+            for (int i = 0; i < NZ; i++) {
+                const T ci = (st == 2 && i == IPSI) ? T(0.5) : cf;      // the k4 psi quirk
+                kacc[i] += wgt * k[i];
+                zs[i] = z[i] + h * ci * k[i];
 #pragma unroll
-            for (int j = 0; j < NSEED; j++) { dacc[i][j] += T(2) * dk[i][j]; Ts[i][j] = S[i][j] + h * T(0.5) * dk[i][j]; }
+                for (int j = 0; j < NSEED; j++) { dacc[i][j] += wgt * dk[i][j]; Ts[i][j] = S[i][j] + h * ci * dk[i][j]; }
+            }
         }
-        // k3
-        rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
-        rhs_tangent(J, Ts, dk);
 #pragma unroll
         for (int i = 0; i < NZ; i++) {
-            kacc[i] += T(2) * k[i];
-            T cf = (i == IPSI) ? T(0.5) : T(1);     // the k4 psi quirk
-            zs[i] = z[i] + h * cf * k[i];
+            z[i] += h / T(6) * kacc[i];
 #pragma unroll
-            for (int j = 0; j < NSEED; j++) { dacc[i][j] += T(2) * dk[i][j]; Ts[i][j] = S[i][j] + h * cf * dk[i][j]; }
-        }
-        // k4
-        rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
-        rhs_tangent(J, Ts, dk);
-#pragma unroll
-        for (int i = 0; i < NZ; i++) {
-            z[i] += h / T(6) * (kacc[i] + k[i]);
-#pragma unroll
-            for (int j = 0; j < NSEED; j++) S[i][j] += h / T(6) * (dacc[i][j] + dk[i][j]);
+            for (int j = 0; j < NSEED; j++) S[i][j] += h / T(6) * dacc[i][j];
         }
     }
 #pragma unroll
@@ -365,8 +361,11 @@ IGT_HDN void mlp_eval_thread(const DevParams<T> &P, T sN, T vN, const T *ctx, T 
 
 // ------------------------------------------------------------------ rows ---------------
 // visit every inequality row of stage k (k == N: terminal node) in workspace order.
-// f(r, c, i0, g0, i1, g1, hxx, hxy, hyy): value, up to two gradient entries in w = (zeta, u)
-// (i1 < 0: single entry), 2x2 Hessian block on (x, y) (collision row, else zeros).
+// f(r, c, IC<i0>, g0, IC<i1>, g1, hxx, hxy, hyy): value, up to two gradient entries in
+// w = (zeta, u) (i1 < 0: single entry), 2x2 Hessian block on (x, y) (collision row only).
+// The indices travel as types so that every use indexes registers statically.
+template <int I> struct IC { static constexpr int value = I; };
+
 template <typename T, typename F>
 IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, const T *u, T ox, T oy, F &&f)
 {
@@ -374,32 +373,33 @@ IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, co
     int r = 0;
     if (k >= 1) {
         if (k < P.N) {
-            f(r++, z[IV] - P.v_max, IV, T(1), -1, Z0, Z0, Z0, Z0);      // mpc.py:317
-            f(r++, P.v_min - z[IV], IV, T(-1), -1, Z0, Z0, Z0, Z0);     // mpc.py:316
+            f(r++, z[IV] - P.v_max, IC<IV>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:317
+            f(r++, P.v_min - z[IV], IC<IV>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);     // mpc.py:316
         }
-        f(r++, z[IEY] - P.ey_lim, IEY, T(1), -1, Z0, Z0, Z0, Z0);      // mpc.py:298
-        f(r++, -P.ey_lim - z[IEY], IEY, T(-1), -1, Z0, Z0, Z0, Z0);    // mpc.py:299
+        f(r++, z[IEY] - P.ey_lim, IC<IEY>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:298
+        f(r++, -P.ey_lim - z[IEY], IC<IEY>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);    // mpc.py:299
         {   // mpc.py:226 in the equivalent distance form d_min - |p - o| <= 0
             T dx = z[IX] - ox, dy = z[IY] - oy;
             T dist = sqrt(dx * dx + dy * dy);
             dist = dist < T(1e-9) ? T(1e-9) : dist;
             T id = T(1) / dist, nx = dx * id, ny = dy * id;
-            f(r++, P.d_min - dist, IX, -nx, IY, -ny, -(T(1) - nx * nx) * id, nx * ny * id, -(T(1) - ny * ny) * id);
+            f(r++, P.d_min - dist, IC<IX>{}, -nx, IC<IY>{}, -ny, -(T(1) - nx * nx) * id, nx * ny * id, -(T(1) - ny * ny) * id);
         }
     }
     if (k == P.N) return;
-    f(r++, u[0] - P.a_max, IUA, T(1), -1, Z0, Z0, Z0, Z0);             // mpc.py:319
-    f(r++, P.a_min - u[0], IUA, T(-1), -1, Z0, Z0, Z0, Z0);            // mpc.py:318
-    f(r++, u[1] - P.df_max, IUD, T(1), -1, Z0, Z0, Z0, Z0);            // mpc.py:321
-    f(r++, -P.df_max - u[1], IUD, T(-1), -1, Z0, Z0, Z0, Z0);          // mpc.py:320
+    f(r++, u[0] - P.a_max, IC<IUA>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);             // mpc.py:319
+    f(r++, P.a_min - u[0], IC<IUA>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:318
+    f(r++, u[1] - P.df_max, IC<IUD>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:321
+    f(r++, -P.df_max - u[1], IC<IUD>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);          // mpc.py:320
     T da = u[0] - up[0], dd = u[1] - up[1];
-    f(r++, da - P.da_max, IPA, T(-1), IUA, T(1), Z0, Z0, Z0);          // mpc.py:303-311
-    f(r++, -da - P.da_max, IPA, T(1), IUA, T(-1), Z0, Z0, Z0);
-    f(r++, dd - P.ddf_max, IPD, T(-1), IUD, T(1), Z0, Z0, Z0);
-    f(r++, -dd - P.ddf_max, IPD, T(1), IUD, T(-1), Z0, Z0, Z0);
+    f(r++, da - P.da_max, IC<IPA>{}, T(-1), IC<IUA>{}, T(1), Z0, Z0, Z0);          // mpc.py:303-311
+    f(r++, -da - P.da_max, IC<IPA>{}, T(1), IC<IUA>{}, T(-1), Z0, Z0, Z0);
+    f(r++, dd - P.ddf_max, IC<IPD>{}, T(-1), IC<IUD>{}, T(1), Z0, Z0, Z0);
+    f(r++, -dd - P.ddf_max, IC<IPD>{}, T(1), IC<IUD>{}, T(-1), Z0, Z0, Z0);
     if (k == P.N - 1)
-        for (int m = 0; m < P.n_cinf; m++)                              // mpc.py:177-180
-            f(r++, P.cinf_A[m][0] * z[IV] + P.cinf_A[m][1] * u[0] - P.cinf_b[m], IV, P.cinf_A[m][0], IUA,
+#pragma unroll 1
+        for (int m = 0; m < P.n_cinf; m++)                                          // mpc.py:177-180
+            f(r++, P.cinf_A[m][0] * z[IV] + P.cinf_A[m][1] * u[0] - P.cinf_b[m], IC<IV>{}, P.cinf_A[m][0], IC<IUA>{},
               P.cinf_A[m][1], Z0, Z0, Z0);
 }
 
@@ -522,14 +522,16 @@ struct Solver {
         else { up[0] = w.U(b, k - 1, 0); up[1] = w.U(b, k - 1, 1); }
     }
 
-    // tracking controller rollout towards cruise speed vt into buffer b; returns the merit
-    IGT_HD T guess_rollout(int b, T vt)
+    // tracking controller rollout towards cruise speed vt; returns the merit
+    // J('mpc' cost) + 100 * sum of row violations (collision in metres).  If u_out is given the
+    // controls are stored there ([N][2] doubles).
+    IGT_HD T guess_rollout(T vt, double *u_out)
     {
         const int N = P.N;
         T z[NZ], up[2] = { uprev[0], uprev[1] };
         T J = T(0), su = T(0), viol = T(0);
 #pragma unroll
-        for (int i = 0; i < NZ; i++) { z[i] = x0[i]; w.Z(b, 0, i) = z[i]; }
+        for (int i = 0; i < NZ; i++) z[i] = x0[i];
         J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
         for (int k = 0; k < N; k++) {
             T K = curvature(z[IS], curv[0], curv[1], curv[2]);
@@ -541,7 +543,7 @@ struct Solver {
             d = fmin(fmax(d, up[1] - P.ddf_max), up[1] + P.ddf_max);
             d = fmin(fmax(d, -P.df_max), P.df_max);
             T u[2] = { a, d };
-            w.U(b, k, 0) = a; w.U(b, k, 1) = d;
+            if (u_out) { u_out[2 * k] = double(a); u_out[2 * k + 1] = double(d); }
             su += a * a + d * d;
             if (k == N - 1)
                 for (int m = 0; m < P.n_cinf; m++)
@@ -549,7 +551,7 @@ struct Solver {
             T zn[NZ];
             rk4_step(P, z, u, curv, zn);
 #pragma unroll
-            for (int i = 0; i < NZ; i++) { z[i] = zn[i]; w.Z(b, k + 1, i) = zn[i]; }
+            for (int i = 0; i < NZ; i++) z[i] = zn[i];
             up[0] = a; up[1] = d;
             J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
             if (k + 1 < N) viol += fmax(T(0), z[IV] - P.v_max) + fmax(T(0), P.v_min - z[IV]);
@@ -561,18 +563,39 @@ struct Solver {
         return J + T(100) * viol;
     }
 
-    // load inputs, pre-check x0, build the initial iterate.  Returns false if finished already.
-    IGT_HD bool init(const ProbIO &io, long p, bool has_ctx, bool has_uinit)
+    IGT_HD void load_inputs(const ProbIO &io, long p, bool has_ctx)
     {
-        const int N = P.N;
         for (int i = 0; i < NZ; i++) x0[i] = T(io.x0[p * NZ + i]);
         uprev[0] = T(io.u_prev[p * 2]); uprev[1] = T(io.u_prev[p * 2 + 1]);
         for (int i = 0; i < 3; i++) curv[i] = T(io.curv[p * 3 + i]);
-        obs = io.obs + p * (N + 1) * 2;
+        obs = io.obs + p * (P.N + 1) * 2;
         gt = has_ctx;
         if (gt) for (int i = 0; i < 4; i++) ctx[i] = T(io.ctx[p * 4 + i]);
+    }
+
+    // cold-start rule: best of N_GUESS tracking rollouts (DESIGN.md "initial guess") -> u_out[N][2]
+    IGT_HD void compute_guess(const ProbIO &io, long p, double *u_out)
+    {
+        load_inputs(io, p, false);
+        const T speeds[N_GUESS] = { T(5.0), T(3.5), T(2.0), T(1.0), T(0.0) };
+        T best = guess_rollout(speeds[0], nullptr);
+        int bestg = 0;
+        for (int g = 1; g < N_GUESS; g++) {
+            T m = guess_rollout(speeds[g], nullptr);
+            if (m < best) { best = m; bestg = g; }
+        }
+        guess_rollout(speeds[bestg], u_out);
+    }
+
+    // load inputs, pre-check x0, build the initial iterate from the controls u_src[N][2]
+    // (warm start or cold-start guess).  Returns false if the problem is finished already.
+    IGT_HD bool init(const ProbIO &io, long p, bool has_ctx, const double *u_src, bool warm)
+    {
+        const int N = P.N;
+        load_inputs(io, p, has_ctx);
         cur = 0; status = 1; iters = 0; ls = 0; need_back = 2; done = false;
-        mu = P.mu0; reg = T(0); alpha = T(1);
+        mu = warm ? P.mu0_warm : P.mu0; reg = T(0); alpha = T(1);
+        const T y_min = warm ? P.y_init_min_warm : P.y_init_min;
         {   // rows on x0 alone: mpc.py:316-317 and :298-299 at k = 0
             T tol = T(1e-9);
             if (!(x0[IV] >= P.v_min - tol && x0[IV] <= P.v_max + tol && fabs(x0[IEY]) <= P.ey_lim + tol)) {
@@ -580,25 +603,15 @@ struct Solver {
                 return false;
             }
         }
-        if (has_uinit) {
+        {
             T z[NZ];
             for (int i = 0; i < NZ; i++) { z[i] = x0[i]; w.Z(0, 0, i) = z[i]; }
             for (int k = 0; k < N; k++) {
-                T u[2] = { T(io.u_init[(p * N + k) * 2]), T(io.u_init[(p * N + k) * 2 + 1]) }, zn[NZ];
+                T u[2] = { T(u_src[2 * k]), T(u_src[2 * k + 1]) }, zn[NZ];
                 w.U(0, k, 0) = u[0]; w.U(0, k, 1) = u[1];
                 rk4_step(P, z, u, curv, zn);
                 for (int i = 0; i < NZ; i++) { z[i] = zn[i]; w.Z(0, k + 1, i) = zn[i]; }
             }
-        } else {
-            // cold-start rule: best of N_GUESS tracking rollouts (DESIGN.md "initial guess")
-            const T speeds[N_GUESS] = { T(5.0), T(3.5), T(2.0), T(1.0), T(0.0) };
-            T best = guess_rollout(0, speeds[0]);
-            int bestg = 0;
-            for (int g = 1; g < N_GUESS; g++) {
-                T m = guess_rollout(1, speeds[g]);
-                if (m < best) { best = m; bestg = g; }
-            }
-            if (bestg != 0) guess_rollout(0, speeds[bestg]);
         }
         // slacks / multipliers, J, sum log y, theta of the initial iterate
         T J = T(0), su = T(0), lg = T(0), th = T(0);
@@ -608,8 +621,8 @@ struct Solver {
             if (k < N) { u[0] = w.U(0, k, 0); u[1] = w.U(0, k, 1); su += u[0] * u[0] + u[1] * u[1]; }
             J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
             int o = row_off(N, P.n_cinf, k);
-            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int, T, int, T, T, T, T) {
-                T y = fmax(-c, P.y_init_min);
+            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto, T, auto, T, T, T, T) {
+                T y = fmax(-c, y_min);
                 w.Y(0, o + r) = y;
                 w.S(0, o + r) = mu / y;
                 lg += log(y);
@@ -651,10 +664,11 @@ struct Solver {
 #pragma unroll
                 for (int i = 0; i < NW; i++) gw[i] = T(0);
                 int o = row_off(N, P.n_cinf, k);
-                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int i0, T g0, int i1, T g1, T, T, T) {
+                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
+                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
                     T s = w.S(b, o + r), y = w.Y(b, o + r);
                     gw[i0] += g0 * s;
-                    if (i1 >= 0) gw[i1] += g1 * s;
+                    if constexpr (i1 >= 0) gw[i1] += g1 * s;
                     rp = fmax(rp, fabs(c + y));
                     s_max = fmax(s_max, s);
                     T sy = s * y;
@@ -723,15 +737,18 @@ struct Solver {
                 Vxx[sym9(IEY, IEY)] = T(2); Vxx[sym9(IEPSI, IEPSI)] = T(2);
                 Vxx[sym9(IS, IS)] -= tcur.Hss; Vxx[sym9(IS, IV)] -= tcur.Hsv; Vxx[sym9(IV, IV)] -= tcur.Hvv;
                 int o = row_off(N, P.n_cinf, N);
-                visit_rows(P, N, z, up, u, ox(N), oy(N), [&](int r, T c, int i0, T g0, int i1, T g1, T hxx, T hxy, T hyy) {
+                visit_rows(P, N, z, up, u, ox(N), oy(N), [&](int r, T c, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
+                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
                     T s = w.S(b, o + r), y = w.Y(b, o + r);
                     T iy = T(1) / y, rhat = s * c + mu, sig = s * iy, gr = s + rhat * iy;
                     Vx[i0] += g0 * gr;
                     Vxx[sym9(i0, i0)] += sig * g0 * g0;
-                    if (i1 >= 0) {
+                    if constexpr (i1 >= 0) {
                         Vx[i1] += g1 * gr;
                         Vxx[sym9(i1, i1)] += sig * g1 * g1;
                         Vxx[sym9(i0, i1)] += sig * g0 * g1;
+                    }
+                    if constexpr (i0 == IX) {
                         Vxx[sym9(IX, IX)] += s * hxx; Vxx[sym9(IX, IY)] += s * hxy; Vxx[sym9(IY, IY)] += s * hyy;
                     }
                 });
@@ -783,15 +800,18 @@ struct Solver {
                     add_dyn_hessian(P, z, u[1], curv, ln, H);
                 }
                 int o = row_off(N, P.n_cinf, k);
-                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int i0, T g0, int i1, T g1, T hxx, T hxy, T hyy) {
+                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
+                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
                     T s = w.S(b, o + r), y = w.Y(b, o + r);
                     T iy = T(1) / y, rhat = s * c + mu, sig = s * iy, gr = s + rhat * iy;
                     g[i0] += g0 * gr;
                     H[sym11(i0, i0)] += sig * g0 * g0;
-                    if (i1 >= 0) {
+                    if constexpr (i1 >= 0) {
                         g[i1] += g1 * gr;
                         H[sym11(i1, i1)] += sig * g1 * g1;
                         H[sym11(i0, i1)] += sig * g0 * g1;
+                    }
+                    if constexpr (i0 == IX) {
                         H[sym11(IX, IX)] += s * hxx; H[sym11(IX, IY)] += s * hxy; H[sym11(IY, IY)] += s * hyy;
                     }
                 });
@@ -830,8 +850,53 @@ struct Solver {
             if (reg > P.reg_max) { status = 3; done = true; return; }
         }
         need_back = 0;
-        alpha = T(1);
         ls = 0;
+        // ---- largest step keeping every slack inside the fraction-to-boundary rule on the
+        //      LINEARISED closed-loop model (d zeta+ = F [d zeta; d u], d u = ku + Ku d zeta)
+        {
+            const T tau = fmax(P.tau_min, T(1) - mu);
+            T a = T(1), dz[NA];
+#pragma unroll
+            for (int i = 0; i < NA; i++) dz[i] = T(0);
+            for (int k = 0; k <= N; k++) {
+                T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
+                load_z(b, k, z); load_up(b, k, up);
+#pragma unroll
+                for (int i = 0; i < NA; i++) dw[i] = dz[i];
+                dw[IUA] = T(0); dw[IUD] = T(0);
+                if (k < N) {
+                    u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1);
+                    T d0 = w.ku(k, 0), d1 = w.ku(k, 1);
+#pragma unroll
+                    for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dz[j]; d1 += w.KK(k, 1, j) * dz[j]; }
+                    dw[IUA] = d0; dw[IUD] = d1;
+                }
+                int o = row_off(N, P.n_cinf, k);
+                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
+                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+                    T y = w.Y(b, o + r);
+                    T dc = g0 * dw[i0];
+                    if constexpr (i1 >= 0) dc += g1 * dw[i1];
+                    T dy = -(c + y) - dc;
+                    if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
+                });
+                if (k == N) break;
+                T S[NZ][NSEED], F[NA][NW];
+#pragma unroll
+                for (int i = 0; i < NZ; i++)
+#pragma unroll
+                    for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
+                build_F(P, S, F);
+#pragma unroll
+                for (int i = 0; i < NA; i++) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int j = 0; j < NW; j++) if (fmask(i, j)) acc += F[i][j] * dw[j];
+                    dz[i] = acc;
+                }
+            }
+            alpha = a * P.alpha_safety;
+        }
     }
 
     // one closed-loop forward pass with step alpha from buffer cur into buffer 1-cur
@@ -859,18 +924,21 @@ struct Solver {
                 dw[IUA] = d0; dw[IUD] = d1;
             }
             int o = row_off(N, P.n_cinf, k);
-            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, int i0, T g0, int i1, T g1, T, T, T) {
+            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
+                constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
                 T s = w.S(b, o + r), y = w.Y(b, o + r);
-                T dc = g0 * dw[i0] + (i1 >= 0 ? g1 * dw[i1] : T(0));
+                T dc = g0 * dw[i0];
+                if constexpr (i1 >= 0) dc += g1 * dw[i1];
                 T yn = y - alpha * (c + y) - dc;
                 T sn = s + (alpha * (s * c + mu) + s * dc) / y;
-                if (yn < (T(1) - tau) * y || sn < (T(1) - tau) * s) fail = true;
+                if (yn < (T(1) - tau) * y) fail = true;                 // fraction to the boundary
+                sn = fmax(sn, (T(1) - tau) * s);                        // multiplier safeguard
                 w.Y(nb, o + r) = yn; w.S(nb, o + r) = sn;
             });
             if (fail) break;
             T un[2] = { u[0] + dw[IUA], u[1] + dw[IUD] };
             // rows at the new point: infeasibility and barrier terms
-            visit_rows(P, k, zn, upn, un, ox(k), oy(k), [&](int r, T c, int, T, int, T, T, T, T) {
+            visit_rows(P, k, zn, upn, un, ox(k), oy(k), [&](int r, T c, auto, T, auto, T, T, T, T) {
                 T yn = w.Y(nb, o + r);
                 th += fabs(c + yn);
                 lg += log(yn);
@@ -959,16 +1027,19 @@ struct Solver {
     }
 };
 
-// Whole solve of problem p, one thread.  (kernels.cu wraps this; tests/hostsim calls it on the CPU.)
+// Whole solve of problem p in workspace slot `slot`, one thread, start to finish.
+// (tests/hostsim calls this on the CPU; the kernels use the persistent-lane driver below.)
 template <typename T>
-IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, long stride, long p,
-                          T *mlp_scratch, int mlp_width)
+IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, long slot, long p,
+                          double *guess_buf, T *mlp_scratch, int mlp_width)
 {
     Solver<T> sv(P);
-    sv.w.base = ws_base; sv.w.stride = stride; sv.w.p = p;
     sv.w.L.init(P.N, P.n_cinf);
+    sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
-    if (sv.init(io, p, io.ctx != nullptr, io.u_init != nullptr)) {
+    const double *u_src = io.u_init ? io.u_init + p * P.N * 2 : guess_buf;
+    if (!io.u_init) sv.compute_guess(io, p, guess_buf);
+    if (sv.init(io, p, io.ctx != nullptr, u_src, io.u_init != nullptr)) {
         sv.terminal_of(sv.cur, sv.tcur, true);
         while (!sv.done) {
             if (sv.need_back) sv.backward();
@@ -980,5 +1051,47 @@ IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, l
     }
     sv.write_out(io, p);
 }
+
+#ifdef __CUDACC__
+// Persistent-lane driver: every thread owns one workspace slot and keeps pulling problems from
+// a global counter until none are left.  All 32 lanes of a warp walk the phases of an iteration
+// (backward sweeps, forward trial, acceptance) together, each lane on its own problem and at
+// its own iteration count, so a slow or failing problem delays only its own lane.
+template <typename T>
+__device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
+                                                 long slot, long B, unsigned long long *counter,
+                                                 const double *guess, T *mlp_scratch, int mlp_width)
+{
+    Solver<T> sv(P);
+    sv.w.L.init(P.N, P.n_cinf);
+    sv.w.bind(ws_base, slot);
+    sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
+    bool active = false, exhausted = false;
+    long p = -1;
+    for (;;) {
+        if (!active && !exhausted) {
+            p = (long)atomicAdd(counter, 1ULL);
+            if (p >= B) exhausted = true;
+            else {
+                const double *u_src = (io.u_init ? io.u_init : guess) + p * P.N * 2;
+                if (sv.init(io, p, io.ctx != nullptr, u_src, io.u_init != nullptr)) {
+                    sv.terminal_of(sv.cur, sv.tcur, true);
+                    active = true;
+                } else {
+                    sv.write_out(io, p);
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, exhausted && !active)) break;
+        if (active && sv.need_back) sv.backward();
+        if (active && !sv.done) {
+            sv.forward_trial();
+            if (sv.trial_ok) sv.terminal_of(1 - sv.cur, sv.tcand, true);
+            sv.finish_trial();
+        }
+        if (active && sv.done) { sv.write_out(io, p); active = false; }
+    }
+}
+#endif
 
 }  // namespace igt

@@ -61,6 +61,7 @@ typedef struct {
     double tol_rp;     /* primal residual |c + slack|_inf (bounds the row violation) */
     double tol_comp;   /* complementarity max(mult*slack) */
     double mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min;
+    double mu0_warm, y_init_min_warm;   /* used instead of mu0 / y_init_min when u_init is given */
     double reg_min, reg_up, reg_down, reg_max;
     double eps_phi, gamma_theta, theta_small;
     int max_iter;      /* mpc.py:137 uses 100*N for IPOPT */

@@ -29,6 +29,8 @@ class CParams(C.Structure):
         ("reg_max", C.c_double), ("eps_phi", C.c_double), ("gamma_theta", C.c_double),
         ("theta_small", C.c_double),
         ("max_iter", C.c_int), ("n_alpha", C.c_int), ("second_order", C.c_int),
+        ("max_ls_fail", C.c_int), ("max_trials", C.c_int), ("predict_alpha", C.c_int),
+        ("alpha_safety", C.c_double),
         ("n_layers", C.c_int), ("dims", C.c_int * (MAX_LAYERS + 1)),
         ("W", _dp * MAX_LAYERS), ("b", _dp * MAX_LAYERS),
         ("Wn", C.c_double * 36), ("mu_f", C.c_double * 6), ("sigma_t", C.c_double), ("mu_t", C.c_double),

@@ -44,6 +44,8 @@ typedef struct {
     double tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min;
     double tau_min, reg_min, reg_up, reg_down, reg_max, eps_phi, gamma_theta, theta_small;
     int max_iter, n_alpha, second_order;
+    int max_ls_fail, max_trials, predict_alpha;
+    double alpha_safety;   /* give up after this many consecutive failed line searches / total forward passes */
     /* gt_mpc value term (mpc.py:326-354,:367-369; model.py:14-67); n_layers = 0 -> 'mpc' mode */
     int n_layers;
     int dims[MAX_MLP_LAYERS + 1];
@@ -517,7 +519,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
             S[w->off[k] + i] = mu / y;
         }
     }
-    int need_jac = 1;
+    int need_jac = 1, ls_fail = 0, trials = 0;
     double stat = 0, rp = 0, s_max = 0, sy_min = 0, sy_max = 0;
     double lxN[NA], lxxN_ss = 0, lxxN_sv = 0, lxxN_vv = 0;
     int it;
@@ -725,9 +727,44 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
         double tau = fmax(P->tau_min, 1.0 - mu);
         int accepted = 0;
         double alpha = 1.0;
+        if (P->predict_alpha) {
+            /* largest step that keeps every slack inside the fraction-to-boundary rule on the
+             * LINEARISED closed-loop model (d zeta+ = F [d zeta; d u], d u = ku + Ku d zeta) */
+            double dz[NA];
+            memset(dz, 0, sizeof(dz));
+            for (int k = 0; k <= N; k++) {
+                double dw[NW];
+                for (int i = 0; i < NA; i++) dw[i] = dz[i];
+                dw[IUA] = dw[IUD] = 0;
+                if (k < N) {
+                    const double *ku = w->ku + 2 * k, *Ku = w->Ku + 2 * NA * k;
+                    double d0 = ku[0], d1 = ku[1];
+                    for (int j = 0; j < NA; j++) { d0 += Ku[j] * dz[j]; d1 += Ku[NA + j] * dz[j]; }
+                    dw[IUA] = d0; dw[IUD] = d1;
+                }
+                int o = w->off[k], n = w->off[k + 1] - o;
+                for (int i = 0; i < n; i++) {
+                    const row_t *r = &w->rows[o + i];
+                    double y = Y[o + i];
+                    double dc = r->g0 * dw[r->i0] + (r->i1 >= 0 ? r->g1 * dw[r->i1] : 0.0);
+                    double dy = -(r->c + y) - dc;
+                    if (dy < 0 && -dy * alpha > tau * y) alpha = tau * y / (-dy);
+                }
+                if (k == N) break;
+                const double *A = w->A + k * NZ * NZ, *B = w->B + k * NZ * 2;
+                for (int i = 0; i < NZ; i++) {
+                    double acc = B[i * 2] * dw[IUA] + B[i * 2 + 1] * dw[IUD];
+                    for (int j = 0; j < NZ; j++) acc += A[i * NZ + j] * dw[j];
+                    dz[i] = acc;
+                }
+                dz[IPA] = dw[IUA]; dz[IPD] = dw[IUD];
+            }
+            alpha *= P->alpha_safety;
+        }
         double *Zn = w->Zn, *Un = w->Un, *Yn = w->Yn, *Sn = w->Sn;
         for (int ls = 0; ls < P->n_alpha; ls++, alpha *= 0.5) {
             int fail = 0;
+            trials++;
             double thetan = 0, lg = 0;
             memcpy(Zn, Z, sizeof(double) * NZ);
             double upn[2] = { pr->u_prev[0], pr->u_prev[1] };
@@ -750,7 +787,8 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                     double dc = r->g0 * dw[r->i0] + (r->i1 >= 0 ? r->g1 * dw[r->i1] : 0.0);
                     double yn = y - alpha * (r->c + y) - dc;
                     double sn = s + (alpha * (s * r->c + mu) + s * dc) / y;
-                    if (yn < (1 - tau) * y || sn < (1 - tau) * s) { fail = 1; break; }
+                    if (yn < (1 - tau) * y) { fail = 1; break; }        /* fraction to the boundary */
+                    if (sn < (1 - tau) * s) sn = (1 - tau) * s;        /* multiplier safeguard */
                     Yn[o + i] = yn; Sn[o + i] = sn;
                 }
                 if (fail || k == N) break;
@@ -786,10 +824,13 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
             memcpy(S, Sn, sizeof(double) * w->M);
             reg = reg > P->reg_min ? reg / P->reg_down : 0.0;
             need_jac = 1;
+            ls_fail = 0;
         } else {
             reg = fmax(reg * P->reg_up, P->reg_min);
-            if (reg > P->reg_max) { status = 4; break; }
+            ls_fail++;
+            if (reg > P->reg_max || ls_fail >= P->max_ls_fail) { status = 4; break; }
         }
+        if (trials >= P->max_trials) { status = 1; break; }
     }
     memcpy(Zout, Z, sizeof(double) * NZ * (N + 1));
     memcpy(Uout, U, sizeof(double) * 2 * N);
@@ -803,9 +844,10 @@ void igt_oracle_default_options(igt_oracle_params *P)
 {
     P->tol = 1e-6; P->tol_rp = 1e-8; P->tol_comp = 1e-7; P->mu0 = 0.3; P->mu_floor = 1e-8;
     P->kappa_eps = 10.0; P->kappa_mu = 0.2; P->theta_mu = 1.5; P->y_init_min = 0.3;
-    P->tau_min = 0.99; P->reg_min = 1e-6; P->reg_up = 10.0; P->reg_down = 10.0; P->reg_max = 1e10;
+    P->tau_min = 0.99; P->reg_min = 1e-4; P->reg_up = 10.0; P->reg_down = 10.0; P->reg_max = 1e10;
     P->eps_phi = 1e-12; P->gamma_theta = 1e-6; P->theta_small = 1e-10;
-    P->max_iter = 300; P->n_alpha = 12; P->second_order = 1;
+    P->max_iter = 300; P->n_alpha = 6; P->second_order = 1;
+    P->max_ls_fail = 1000; P->max_trials = 1000000; P->predict_alpha = 1; P->alpha_safety = 0.99;
 }
 
 size_t igt_oracle_params_size(void) { return sizeof(igt_oracle_params); }

@@ -37,15 +37,17 @@ class Options:
     theta_mu = 1.5
     y_init_min = 0.3
     tau_min = 0.99
-    reg_min = 1e-6
+    reg_min = 1e-4
     reg_up = 10.0
     reg_down = 10.0
     reg_max = 1e10
-    n_alpha = 12
+    n_alpha = 6
     eps_phi = 1e-12
     gamma_theta = 1e-6
     theta_small = 1e-10
     second_order = True
+    predict_alpha = True
+    alpha_safety = 0.99
 
 
 # --------------------------------------------------------------------------------------
@@ -360,6 +362,24 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
         tau = max(opt.tau_min, 1.0 - mu)
         accepted = False
         alpha = 1.0
+        if opt.predict_alpha:
+            # largest step keeping every slack inside the fraction-to-boundary rule on the
+            # linearised closed-loop model
+            dz = np.zeros(9)
+            for k in range(N + 1):
+                c = rows[k][0]
+                dy = ky[k] + Ky[k] @ dz
+                neg = dy < 0
+                if np.any(neg):
+                    alpha = min(alpha, np.min(tau * Y[k][neg] / (-dy[neg])))
+                if k == N:
+                    break
+                du = ku[k] + Ku[k] @ dz
+                dzn = np.zeros(9)
+                dzn[:7] = A[k] @ dz[:7] + B[k] @ du
+                dzn[7:] = du
+                dz = dzn
+            alpha *= opt.alpha_safety
         for _ in range(opt.n_alpha):
             Zn = np.empty_like(Z); Un = np.empty_like(U)
             Yn = [None] * (N + 1); Sn = [None] * (N + 1)
@@ -371,9 +391,10 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
                 dz = np.concatenate([Zn[k] - Z[k], upn - up])
                 Yn[k] = Y[k] + alpha * ky[k] + Ky[k] @ dz
                 Sn[k] = S[k] + alpha * ks[k] + Ks[k] @ dz
-                if np.any(Yn[k] < (1 - tau) * Y[k]) or np.any(Sn[k] < (1 - tau) * S[k]):
+                if np.any(Yn[k] < (1 - tau) * Y[k]):             # fraction to the boundary
                     fail = True
                     break
+                Sn[k] = np.maximum(Sn[k], (1 - tau) * S[k])      # multiplier safeguard
                 if k == N:
                     break
                 Un[k] = U[k] + alpha * ku[k] + Ku[k] @ dz

@@ -32,10 +32,11 @@ static int run(const igt_params *p, int B, const double *x0, const double *u_pre
         P.sigma_t = T(sigma_t); P.mu_t = T(mu_t);
     }
     WsLayout L; L.init(p->N, p->n_cinf);
-    std::vector<T> ws((size_t)L.total * B);
+    std::vector<T> ws((size_t)L.total * 32);
     std::vector<T> scratch((size_t)12 * width);
+    std::vector<double> guess((size_t)2 * p->N);
     ProbIO io = { x0, u_prev, curv, obs, ctx, u_init, x, u, cost, viol, status, iters };
-    for (long q = 0; q < B; q++) solve_problem<T>(P, io, ws.data(), B, q, scratch.data(), width);
+    for (long q = 0; q < B; q++) solve_problem<T>(P, io, ws.data(), q % 32, q, guess.data(), scratch.data(), width);
     return 0;
 }
 

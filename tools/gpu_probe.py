@@ -1,4 +1,4 @@
-"""Quick GPU probe: throughput of the solver kernel at several batch sizes / precisions."""
+"""Quick GPU probe: throughput of the solver kernel.  usage: gpu_probe.py B [f64|f32|both] [reps]"""
 import sys, time, os
 import numpy as np
 import torch
@@ -8,22 +8,29 @@ from igt_mpc_int_b200.planner import BatchSolver
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+    precs = ("f64", "f32") if len(sys.argv) < 3 or sys.argv[2] == "both" else (sys.argv[2],)
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     N = 40
-    t0 = time.time(); pb = S.mid_episode(B, N=N); print("gen", time.time() - t0, flush=True)
+    cache = f"/tmp/pb_{B}.npz"
+    if os.path.exists(cache):
+        d = np.load(cache); x0, up, cv, ob = d["x0"], d["up"], d["cv"], d["ob"]
+    else:
+        pb = S.mid_episode(B, N=N); x0, up, cv, ob = pb.x0, pb.u_prev, pb.curv, pb.obs
+        np.savez(cache, x0=x0, up=up, cv=cv, ob=ob)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    x0, up, cv, ob = t(pb.x0), t(pb.u_prev), t(pb.curv), t(pb.obs)
-    for prec in ("f64", "f32"):
-        for bsz in (B,):
-            s = BatchSolver(N=N, precision=prec)
-            out = s.solve_batch_device(x0[:bsz], up[:bsz], cv[:bsz], ob[:bsz]); torch.cuda.synchronize()
+    x0, up, cv, ob = t(x0), t(up), t(cv), t(ob)
+    for prec in precs:
+        s = BatchSolver(N=N, precision=prec)
+        out = s.solve_batch_device(x0, up, cv, ob); torch.cuda.synchronize()
+        for _ in range(reps):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(); out = s.solve_batch_device(x0[:bsz], up[:bsz], cv[:bsz], ob[:bsz], out=out); ev1.record(); torch.cuda.synchronize()
+            ev0.record(); out = s.solve_batch_device(x0, up, cv, ob, out=out); ev1.record(); torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1)
             st = out["status"].cpu().numpy(); it = out["iters"].cpu().numpy()
             conv = (st == 0).sum()
-            print(f"{prec} B={bsz} ms={ms:.1f} converged={conv} ({conv/bsz:.3f}) solves/s={conv/ms*1e3:.0f} "
-                  f"iters med={np.median(it[st==0])} p90={np.percentile(it[st==0],90)} max={it.max()} status={np.bincount(st, minlength=5)}", flush=True)
-            s.close()
+            print(f"{prec} B={B} ms={ms:.1f} converged={conv} ({conv/B:.3f}) solves/s={conv/ms*1e3:.0f} "
+                  f"iters med={np.median(it[st==0])} p90={np.percentile(it[st==0],90)} sum={it.sum()} status={np.bincount(st, minlength=5)}", flush=True)
+        s.close()
 
 if __name__ == "__main__":
     main()
