@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- converged MPC solves/sec of the batched solver (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (cold-start guess kernel + persistent solver kernel) over
+one batch of synthetic problems.  Default workload = BASELINE.json configs[1]: 'mpc' mode,
+scenarios 1-8, 4096 synthetic initial conditions per scenario (32768 problems), horizon N=40,
+on ONE B200; with --gpus N every rank solves its own batch of that size (weak scaling; no
+data-path collective -- NCCL only gathers the counters).
+
+value   = converged solves/s, inputs resident in HBM, CUDA events around the kernels
+e2e     = same metric through the host-pointer C ABI call (igt_solve_host): pinned host buffers,
+          H2D of the inputs and D2H of x, u, cost, viol, status, iters inside the timed region
+--impl reference: the reference's own solver (CasADi/IPOPT) cannot run offline, so this arm times
+          the oracle's fp64 C restatement of the same NLP/algorithm on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "converged MPC solves/sec"
+UNIT = "solves/s"
+
+WORKLOADS = {
+    # name: (generator, problems per GPU, horizon, mode)
+    "cfg2_mpc_sc1-8_4096ic": ("mid_episode", 32768, 40, "mpc"),
+    "cfg2_episode_start": ("episode_start", 32768, 40, "mpc"),
+    "cfg4_frenet_65536": ("mid_episode", 65536, 40, "mpc"),
+    "cfg5_131072_N40": ("mid_episode", 131072, 40, "mpc"),
+    "cfg5_131072_N20": ("mid_episode", 131072, 20, "mpc"),
+    "cfg5_131072_N10": ("mid_episode", 131072, 10, "mpc"),
+    "cfg3_gt_mpc_16384": ("mid_episode", 16384, 40, "gt_mpc"),
+}
+DEFAULT_WORKLOAD = "cfg2_mpc_sc1-8_4096ic"
+
+
+def make_problems(name, rank):
+    from igt_mpc_int_b200 import scenarios as S
+    gen, B, N, mode = WORKLOADS[name]
+    seed = {"cfg4_frenet_65536": 4}.get(name, 2026) + 1000 * rank      # seeds 2026+sc / 4
+    cache = os.path.join("/tmp", "igt_bench_%s_r%d.npz" % (name, rank))
+    if os.path.exists(cache):
+        d = np.load(cache)
+        return d["x0"], d["up"], d["cv"], d["ob"], d["ctx"], N, mode
+    pb = getattr(S, gen)(B, N=N, seed=seed)
+    try:
+        np.savez(cache, x0=pb.x0, up=pb.u_prev, cv=pb.curv, ob=pb.obs, ctx=pb.nn_ctx)
+    except OSError:
+        pass
+    return pb.x0, pb.u_prev, pb.curv, pb.obs, pb.nn_ctx, N, mode
+
+
+def random_mlp(hidden=(128, 128), seed=2026):
+    """Random-init value network, torch.nn.Linear default init in fp64."""
+    import torch
+    torch.manual_seed(seed)
+    dims = [6] + list(hidden) + [1]
+    layers = [torch.nn.Linear(dims[i], dims[i + 1], dtype=torch.double) for i in range(len(dims) - 1)]
+    weights = [(l.weight.detach().numpy().copy(), l.bias.detach().numpy().copy()) for l in layers]
+    return dict(weights=weights, Wn=np.eye(6), mu_f=np.zeros(6), sigma_t=1.0, mu_t=0.0)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons}
+
+
+def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0):
+    """The oracle's C restatement timed on the host cores on the first n_sample problems."""
+    from oracle import nlp, c_oracle
+    P = nlp.Params(N=N)
+    term = None
+    if mode == "gt_mpc":
+        term = nlp.MLPTerm(weights=mlp["weights"], Wn=mlp["Wn"], mu_f=mlp["mu_f"], sigma_t=mlp["sigma_t"], mu_t=mlp["mu_t"])
+    co = c_oracle.COracle(P, term, max_iter=max_iter)
+    co.solve(x0[:64], up[:64], cv[:64], ob[:64], n_threads=threads)           # warm the library / page in
+    t0 = time.perf_counter()
+    r = co.solve(x0[:n_sample], up[:n_sample], cv[:n_sample], ob[:n_sample], n_threads=threads)
+    dt = time.perf_counter() - t0
+    return int((r["status"] == 0).sum()), dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: CPU arm (rank 0 only)."""
+    if rank != 0:
+        return
+    x0, up, cv, ob, ctx, N, mode = make_problems(args.workload, 0)
+    mlp = random_mlp() if mode == "gt_mpc" else None
+    cores = os.cpu_count() or 1
+    n_sample = min(len(x0), max(256, 64 * cores))
+    for _ in range(args.warmup):
+        cpu_baseline(x0, up, cv, ob, N, mode, mlp, min(256, n_sample), 60)
+    conv, tsum = 0, 0.0
+    for _ in range(args.steps):
+        c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, 60)
+        conv += c
+        tsum += dt
+    val = conv / tsum
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "horizon": N, "mode": mode, "problems_per_step": n_sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "first %d problems of the workload per step, all host threads; the reference's "
+                                   "CasADi/IPOPT solver is not installable offline, so the oracle's fp64 C restatement "
+                                   "of the same NLP is timed" % n_sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the solver has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from igt_mpc_int_b200.planner import BatchSolver
+    x0, up, cv, ob, ctx, N, mode = make_problems(args.workload, rank)
+    B = len(x0)
+    mlp = random_mlp() if mode == "gt_mpc" else None
+    solver = BatchSolver(N=N, precision=args.precision, mlp=mlp)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dx0, dup, dcv, dob = t(x0), t(up), t(cv), t(ob)
+    dctx = t(ctx) if mode == "gt_mpc" else None
+    out = solver.solve_batch_device(dx0, dup, dcv, dob, nn_ctx=dctx)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver.solve_batch_device(dx0, dup, dcv, dob, nn_ctx=dctx, out=out)
+    barrier()
+
+    # ---- device-resident timing: CUDA events around every step, L2 flushed between steps ----
+    l0 = solver.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        flush.zero_()
+        e0.record()
+        solver.solve_batch_device(dx0, dup, dcv, dob, nn_ctx=dctx, out=out)
+        e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    launches = solver.launches - l0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    dev_ms = float(sum(step_ms))
+    status = out["status"].cpu().numpy()
+    iters = out["iters"].cpu().numpy()
+    conv_per_step = int((status == 0).sum())
+    stats = torch.tensor([dev_ms, float(conv_per_step), float(iters.sum()), float(B)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_max, conv_all, iters_all, B_all = mx[0].item(), sm[1].item(), sm[2].item(), sm[3].item()
+    else:
+        dev_ms_max, conv_all, iters_all, B_all = dev_ms, float(conv_per_step), float(iters.sum()), float(B)
+    value = conv_all * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- end-to-end: host-pointer C ABI call with pinned host buffers ----
+    hin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x0, up, cv, ob)]
+    hctx = torch.from_numpy(np.ascontiguousarray(ctx)).pin_memory() if mode == "gt_mpc" else None
+    hout = dict(x=torch.empty((B, N + 1, 7), dtype=torch.float64).pin_memory(),
+                u=torch.empty((B, N, 2), dtype=torch.float64).pin_memory(),
+                cost=torch.empty(B, dtype=torch.float64).pin_memory(), viol=torch.empty(B, dtype=torch.float64).pin_memory(),
+                status=torch.empty(B, dtype=torch.int32).pin_memory(), iters=torch.empty(B, dtype=torch.int32).pin_memory())
+    hout_np = {k: v.numpy() for k, v in hout.items()}
+    hin_np = [a.numpy() for a in hin]
+    h2d = sum(a.nbytes for a in hin_np) + (hctx.numpy().nbytes if hctx is not None else 0)
+    d2h = sum(v.nbytes for v in hout_np.values())
+    e2e_steps = max(3, min(args.steps, 5))
+    solver.solve_batch(*hin_np, nn_ctx=None if hctx is None else hctx.numpy(), out=hout_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.solve_batch(*hin_np, nn_ctx=None if hctx is None else hctx.numpy(), out=hout_np)
+    torch.cuda.synchronize()
+    e2e_t = time.perf_counter() - t0
+    e2e_conv = int((hout_np["status"] == 0).sum())
+    e2e_stats = torch.tensor([e2e_t, float(e2e_conv)], dtype=torch.float64, device=dev)
+    if world > 1:
+        a = e2e_stats.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = e2e_stats.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_t, e2e_conv_all = a[0].item(), b[1].item()
+    else:
+        e2e_conv_all = float(e2e_conv)
+    e2e_value = e2e_conv_all * e2e_steps / e2e_t
+
+    if rank == 0:
+        # ---- rooflines ----
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        kernel_ms = dev_ms / args.steps                       # solver + guess kernels of one step on this rank
+        alg_bytes = 8.0 * (11 * N + 24) * B                   # 4(11N+24) B/solve for fp32 I/O; ours is fp64
+        achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        alg_flops = float(iters.sum()) * N * 1.4e4            # 1.4e4 FLOP per stage-iteration
+        fma_peak = solver.measure_fma_peak()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": args.workload, "horizon": N, "mode": mode, "problems_per_gpu_per_step": B,
+                       "l2": "flushed (256 MiB memset) between timed steps", "warm_start": False,
+                       "parallelism": "dp%d (independent problems, no data-path collective)" % world},
+            "converged_fraction": conv_all / B_all, "mean_iterations": iters_all / B_all,
+            "p50_step_latency_ms": float(np.median(step_ms)), "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "note": "algorithmic bytes 8*(11N+24) per solve; the solver is CUDA-core/latency bound, "
+                                 "see compute_roofline (SURVEY 8(d))"},
+            "compute_roofline": {"bound": "%s-fma" % args.precision, "achieved": alg_flops / (kernel_ms * 1e-3) / 1e12,
+                                 "peak": fma_peak, "unit": "TFLOP/s",
+                                 "frac": alg_flops / (kernel_ms * 1e-3) / 1e12 / fma_peak,
+                                 "note": "algorithmic 1.4e4 FLOP per stage-iteration x measured iterations; peak = "
+                                         "dependent-free FMA chains measured on this GPU in this run"},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_sample = min(B, max(512, 128 * cores))
+            c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, solver.params.max_iter)
+            line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "first %d problems of the same batch, oracle fp64 C restatement on all "
+                                              "host threads (the reference's CasADi/IPOPT solver is not installable "
+                                              "offline)" % n_sample}
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

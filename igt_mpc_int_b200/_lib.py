@@ -10,11 +10,12 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libigtmpc.so")
+LIB_PATH = os.environ.get("IGT_LIB", os.path.join(_HERE, "lib", "libigtmpc.so"))   # IGT_LIB: developer override
 
 MAX_CINF, MAX_LAYERS = 128, 5
 PREC_F32, PREC_F64 = 0, 1
-STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "x0_infeasible", 3: "reg_limit", 4: "line_search"}
+STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "x0_infeasible", 3: "reg_limit", 4: "line_search",
+                5: "stalled_infeasible"}
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -38,7 +39,8 @@ class IgtParams(C.Structure):
         ("mu0_warm", C.c_double), ("y_init_min_warm", C.c_double),
         ("reg_min", C.c_double), ("reg_up", C.c_double), ("reg_down", C.c_double), ("reg_max", C.c_double),
         ("eps_phi", C.c_double), ("gamma_theta", C.c_double), ("theta_small", C.c_double),
-        ("max_iter", C.c_int), ("n_alpha", C.c_int), ("second_order", C.c_int), ("precision", C.c_int),
+        ("max_iter", C.c_int), ("n_alpha", C.c_int), ("second_order", C.c_int),
+        ("stall_iter", C.c_int), ("stall_rp", C.c_double), ("precision", C.c_int),
     ]
 
     def set_cinf(self, A, b):
@@ -60,7 +62,7 @@ _lib = None
 
 EXPORTS = ("igt_version", "igt_default_params", "igt_create", "igt_destroy", "igt_last_error",
            "igt_set_mlp", "igt_rollout_dev", "igt_rollout_host", "igt_eval_host", "igt_solve_dev",
-           "igt_solve_host", "igt_launch_count")
+           "igt_solve_host", "igt_launch_count", "igt_measure_fma_peak")
 
 
 def load():
@@ -87,6 +89,8 @@ def load():
     lib.igt_solve_dev.argtypes = [vp, C.c_int] + [vp] * 12 + [vp]
     lib.igt_solve_host.argtypes = [vp, C.c_int] + [vp] * 12
     lib.igt_launch_count.argtypes = [vp]
+    lib.igt_measure_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.igt_measure_fma_peak.restype = C.c_int
     lib.igt_launch_count.restype = C.c_longlong
     for f in ("igt_default_params", "igt_create", "igt_set_mlp", "igt_rollout_dev", "igt_rollout_host",
               "igt_eval_host", "igt_solve_dev", "igt_solve_host"):

@@ -21,10 +21,11 @@
 
 using namespace igt;
 
-// resident solver threads per SM (255 registers/thread -> 4 blocks of 64)
-#ifndef SLOTS_PER_SM
-#define SLOTS_PER_SM 256
+// resident solver threads per SM: one CTA of SOLVE_BLOCK threads (255 registers/thread -> 256 threads)
+#ifndef SOLVE_BLOCK
+#define SOLVE_BLOCK 256
 #endif
+#define SLOTS_PER_SM SOLVE_BLOCK
 
 // ------------------------------------------------------------------ device constants ----
 __constant__ DevParams<float> c_Pf;
@@ -47,13 +48,12 @@ __global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *g
 }
 
 template <typename T>
-__global__ void __launch_bounds__(64) solve_kernel(ProbIO io, T *ws, long n_slots, long B,
-                                                   unsigned long long *counter, const double *guess,
-                                                   T *mlp_scratch, int mlp_width)
+__global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws, long n_slots, long B, Sched sc,
+                                                   const double *guess, T *mlp_scratch, int mlp_width)
 {
     long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;   // grid is sized to n_slots exactly
     const DevParams<T> &P = ConstP<T>::get();
-    solve_persistent<T>(P, io, ws, slot, B, counter, guess,
+    solve_persistent<T>(P, io, ws, slot, B, sc, guess,
                         mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width);
 }
 
@@ -89,19 +89,20 @@ __global__ void __launch_bounds__(128) rollout_kernel(int B, const float *__rest
         }
         // compensated value step
         Slip<float> sl = slip_of(P, u[1]);
+        const AngleBase<float> ab = angle_base(sl, z);
         for (int it = 0; it < P.n_rk; it++) {
             float zs[NZ], k1[NZ], k2[NZ], k3[NZ], k4[NZ];
-            rhs<float, false>(P, z, u[0], sl, curv, k1, nullptr);
+            rhs<float, false>(P, z, u[0], sl, ab, curv, k1, nullptr);
 #pragma unroll
             for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * 0.5f * k1[i];
-            rhs<float, false>(P, zs, u[0], sl, curv, k2, nullptr);
+            rhs<float, false>(P, zs, u[0], sl, ab, curv, k2, nullptr);
 #pragma unroll
             for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * 0.5f * k2[i];
-            rhs<float, false>(P, zs, u[0], sl, curv, k3, nullptr);
+            rhs<float, false>(P, zs, u[0], sl, ab, curv, k3, nullptr);
 #pragma unroll
             for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * k3[i];
             zs[IPSI] = z[IPSI] + h * 0.5f * k3[IPSI];
-            rhs<float, false>(P, zs, u[0], sl, curv, k4, nullptr);
+            rhs<float, false>(P, zs, u[0], sl, ab, curv, k4, nullptr);
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 float inc = h / 6.f * (k1[i] + 2.f * k2[i] + 2.f * k3[i] + k4[i]);
@@ -184,6 +185,20 @@ __global__ void __launch_bounds__(128) eval_kernel(long B, const double *__restr
     }
     cost[p] = J;
     viol[p] = m;
+}
+
+// dependent-free FMA chains: the CUDA-core roofline denominator that MEASURED_PEAKS.json lacks
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters)
+{
+    T a0 = T(threadIdx.x) * T(1e-3), a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
+    T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
+    const T m = T(0.999999), c = T(1e-6);
+    for (int i = 0; i < iters; i++) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    out[(long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 // ------------------------------------------------------------------ handle --------------
@@ -371,7 +386,7 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     WsLayout L; L.init(h->prm.N, h->prm.n_cinf);
     size_t esz = f64 ? 8 : 4;
     // persistent lanes: at most SLOTS_PER_SM threads per SM, never more than problems
-    const int bs = 64;
+    const int bs = SOLVE_BLOCK;
     long max_slots = (long)h->n_sm * SLOTS_PER_SM;
     long n_slots = ((B + bs - 1) / bs) * (long)bs;
     if (n_slots > max_slots) n_slots = max_slots;
@@ -381,13 +396,21 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
         rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * n_slots * esz);
         if (rc) return rc;
     }
-    rc = grow(h, &h->guess, &h->guess_bytes, 256 + (size_t)B * h->prm.N * 2 * sizeof(double));
+    // scheduler block: [counter, q_head, q_tail, in_flight | queue[n_slots] | save_i | save_t], then the guesses
+    size_t off_queue = 256, off_savei = off_queue + ((size_t)n_slots * 4 + 255) / 256 * 256;
+    size_t off_savet = off_savei + (size_t)n_slots * SAVE_I * 8, off_guess = off_savet + (size_t)n_slots * SAVE_T * 8;
+    rc = grow(h, &h->guess, &h->guess_bytes, off_guess + (size_t)B * h->prm.N * 2 * sizeof(double));
     if (rc) return rc;
-    unsigned long long *counter = (unsigned long long *)h->guess;
-    double *guess = (double *)((char *)h->guess + 256);
+    char *sb = (char *)h->guess;
+    Sched sc;
+    sc.counter = (unsigned long long *)sb; sc.q_head = (int *)(sb + 8); sc.q_tail = (int *)(sb + 12);
+    sc.in_flight = (int *)(sb + 16); sc.queue = (int *)(sb + off_queue);
+    sc.save_i = (long long *)(sb + off_savei); sc.save_t = (double *)(sb + off_savet);
+    double *guess = (double *)(sb + off_guess);
     rc = upload_params(h, st, !f64, f64);
     if (rc) return rc;
-    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(sb, 0, 256, st));
+    CK(cudaMemsetAsync(sc.queue, 0xFF, (size_t)n_slots * 4, st));
     ProbIO io = { x0, u_prev, curv, obs_xy, nn_ctx, u_init, x, u, cost, viol, status, iters };
     if (!u_init) {
         int gbs = 128, ggs = (B + gbs - 1) / gbs;
@@ -396,9 +419,9 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
         h->launches++;
     }
     int gs = (int)(n_slots / bs);
-    if (f64) solve_kernel<double><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, counter, guess,
+    if (f64) solve_kernel<double><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
                                                      nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width);
-    else solve_kernel<float><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, counter, guess,
+    else solve_kernel<float><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
                                                 nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width);
     h->launches++;
     CK(cudaGetLastError());
@@ -484,4 +507,30 @@ int igt_eval_host(igt_handle *h, int B, const double *x0, const double *u_prev, 
     return IGT_OK;
 }
 
+int igt_measure_fma_peak(igt_handle *h, int precision, double *tflops)
+{
+    if (!h || !tflops) return IGT_EINVAL;
+    const int blocks = h->n_sm * 8, threads = 256, iters = 1 << 16;
+    int rc = grow(h, &h->stage, &h->stage_bytes, (size_t)blocks * threads * 8);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0));
+        if (precision == IGT_PREC_F64) fma_peak_kernel<double><<<blocks, threads>>>((double *)h->stage, iters);
+        else fma_peak_kernel<float><<<blocks, threads>>>((float *)h->stage, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+        h->launches++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return IGT_OK;
+}
+
 }  // extern "C"
+

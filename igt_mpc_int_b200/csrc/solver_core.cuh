@@ -40,11 +40,11 @@ constexpr int N_GUESS = 5;
 
 template <typename T>
 struct DevParams {
-    int N, n_rk, n_cinf, max_iter, n_alpha, second_order, n_layers;
+    int N, n_rk, n_cinf, max_iter, n_alpha, second_order, n_layers, stall_iter;
     int dims[MAX_MLP_LAYERS + 1];
     T dt, h, l_r, lsum, inv_lr, rho;
     T v_min, v_max, a_min, a_max, df_max, ey_lim, da_max, ddf_max, d_min, w_u;
-    T tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min, mu0_warm, y_init_min_warm, alpha_safety;
+    T tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min, mu0_warm, y_init_min_warm, alpha_safety, stall_rp;
     T reg_min, reg_up, reg_down, reg_max, eps_phi, gamma_theta, theta_small;
     T cinf_A[MAX_CINF][2], cinf_b[MAX_CINF];
     T Wn[36], mu_f[6], sigma_t, mu_t;
@@ -94,6 +94,12 @@ struct Ws {
     WsLayout L;
     IGT_HD void bind(T *base, long slot) { wb = base + (slot / 32) * (long)L.total * 32 + (slot % 32); }
     IGT_HD T &at(int e) const { return wb[e * 32]; }
+    IGT_HD void pf(int e) const
+    {
+#ifdef __CUDA_ARCH__
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + e * 32));
+#endif
+    }
     IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ[b] + k * NZ + i); }
     IGT_HD T &U(int b, int k, int i) const { return at(L.oU[b] + k * 2 + i); }
     IGT_HD T &Y(int b, int r) const { return at(L.oY[b] + r); }
@@ -135,18 +141,53 @@ IGT_HD T curvature(T s, T b0, T b1, T kv)
     return (s >= b0 ? kv : T(0)) - (s >= b1 ? kv : T(0));
 }
 
+// sin/cos of (a + d) from sin/cos of a for the small within-step drift d of epsi and psi:
+// one MPC step evaluates the right-hand side 16 times at angles that differ from the step's
+// start by < 0.1 rad, so two full-range sincos per step plus 16 short polynomials replace 32
+// full-range fp64 sincos calls (40 % of all executed instructions in the first profile).
+// |d| <= 0.25: Taylor to d^15 / d^14, truncation error < 1e-20; beyond that the library path.
+template <typename T>
+struct AngleBase { T e0, p0, a1, a2, s1b, c1b, spb, cpb; };
+
+IGT_HD void rot_small(double, double sa, double ca, double d, double *s, double *c)
+{
+    if (fabs(d) > 0.25) {
+        double sd, cd;
+        sincos(d, &sd, &cd);
+        *s = sa * cd + ca * sd; *c = ca * cd - sa * sd;
+        return;
+    }
+    double d2 = d * d;
+    double sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880 + d2 * (-1.0 / 39916800 + d2 * (1.0 / 6227020800.0 + d2 * (-1.0 / 1307674368000.0))))))));
+    double cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320 + d2 * (-1.0 / 3628800 + d2 * (1.0 / 479001600.0 + d2 * (-1.0 / 87178291200.0)))))));
+    *s = sa * cd + ca * sd;
+    *c = ca * cd - sa * sd;
+}
+IGT_HD void rot_small(float a, float, float, float d, float *s, float *c) { sincosf(a + d, s, c); }   // MUFU-fast already
+
+template <typename T>
+IGT_HD AngleBase<T> angle_base(const Slip<T> &sl, const T *z0)
+{
+    AngleBase<T> ab;
+    ab.e0 = z0[IEPSI]; ab.p0 = z0[IPSI];
+    ab.a1 = sl.beta + ab.e0; ab.a2 = ab.p0 + sl.beta;
+    sincos_t(ab.a1, &ab.s1b, &ab.c1b);
+    sincos_t(ab.a2, &ab.spb, &ab.cpb);
+    return ab;
+}
+
 // zdot (planner order) and, if JAC, the 13 state + 6 steering partials
 template <typename T>
 struct RhsJac { T s_ey, s_epsi, s_v, s_d, ey_epsi, ey_v, ey_d, e_ey, e_epsi, e_v, e_d, x_v, x_psi, x_d, y_v, y_psi, y_d, p_v, p_d; };
 
 template <typename T, bool JAC>
-IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const T *curv, T *zd, RhsJac<T> *J)
+IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const AngleBase<T> &ab, const T *curv, T *zd, RhsJac<T> *J)
 {   // kinematic_bicycle_model_frenet.py:71-91
     T ey = z[IEY], epsi = z[IEPSI], v = z[IV], psi = z[IPSI];
     T K = curvature(z[IS], curv[0], curv[1], curv[2]);
     T c1, s1, cp, sp;
-    sincos_t(sl.beta + epsi, &s1, &c1);
-    sincos_t(psi + sl.beta, &sp, &cp);
+    rot_small(ab.a1, ab.s1b, ab.c1b, epsi - ab.e0, &s1, &c1);
+    rot_small(ab.a2, ab.spb, ab.cpb, psi - ab.p0, &sp, &cp);
     T iden = T(1) / (T(1) - K * ey);
     T sdot = v * c1 * iden;
     T yaw = v * sl.sb * P.inv_lr;
@@ -181,6 +222,7 @@ IGT_HDN void rk4_step(const DevParams<T> &P, const T *z0, const T *u, const T *c
 {
     const T h = P.h;
     Slip<T> sl = slip_of(P, u[1]);
+    const AngleBase<T> ab = angle_base(sl, z0);
     T z[NZ], zs[NZ], k[NZ], kacc[NZ];
 #pragma unroll
     for (int i = 0; i < NZ; i++) z[i] = z0[i];
@@ -190,7 +232,7 @@ IGT_HDN void rk4_step(const DevParams<T> &P, const T *z0, const T *u, const T *c
         for (int i = 0; i < NZ; i++) { zs[i] = z[i]; kacc[i] = T(0); }
 #pragma unroll 1
         for (int st = 0; st < 4; st++) {
-            rhs<T, false>(P, zs, u[0], sl, curv, k, nullptr);
+            rhs<T, false>(P, zs, u[0], sl, ab, curv, k, nullptr);
             const T wgt = (st == 0 || st == 3) ? T(1) : T(2);
             const T cf = (st == 2) ? T(1) : T(0.5);
 #pragma unroll
@@ -231,6 +273,7 @@ IGT_HDN void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u, const
 {
     const T h = P.h;
     Slip<T> sl = slip_of(P, u[1]);
+    const AngleBase<T> ab = angle_base(sl, z0);
     T z[NZ], zs[NZ], k[NZ], kacc[NZ];
     T Ts[NZ][NSEED], dk[NZ][NSEED], dacc[NZ][NSEED];
     RhsJac<T> J;
@@ -251,7 +294,7 @@ IGT_HDN void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u, const
         }
 #pragma unroll 1
         for (int st = 0; st < 4; st++) {
-            rhs<T, true>(P, zs, u[0], sl, curv, k, &J);
+            rhs<T, true>(P, zs, u[0], sl, ab, curv, k, &J);
             rhs_tangent(J, Ts, dk);
             const T wgt = (st == 0 || st == 3) ? T(1) : T(2);
             const T cf = (st == 2) ? T(1) : T(0.5);
@@ -358,6 +401,18 @@ IGT_HDN void mlp_eval_thread(const DevParams<T> &P, T sN, T vN, const T *ctx, T 
         out.gs = out.gv = out.Hss = out.Hsv = out.Hvv = T(0);
     }
 }
+
+// sum of log(y_i) with one log per LOGCHUNK factors (slacks lie in [1e-11, 1e3], so a product of
+// 16 stays far inside the fp64 range; fp32 uses 3)
+template <typename T> struct LogChunk { static constexpr int n = 16; };
+template <> struct LogChunk<float> { static constexpr int n = 3; };
+template <typename T>
+struct LogSum {
+    T sum, prod; int cnt;
+    IGT_HD LogSum() : sum(T(0)), prod(T(1)), cnt(0) {}
+    IGT_HD void add(T y) { prod *= y; if (++cnt == LogChunk<T>::n) { sum += log(prod); prod = T(1); cnt = 0; } }
+    IGT_HD T total() const { return cnt ? sum + log(prod) : sum; }
+};
 
 // ------------------------------------------------------------------ rows ---------------
 // visit every inequality row of stage k (k == N: terminal node) in workspace order.
@@ -511,6 +566,32 @@ struct Solver {
         }
     }
 
+    // software prefetch of stage k's workspace rows (the sweeps stream ~1.6 GB of workspace per
+    // launch; issuing the next stage's lines early hides most of the HBM/L2 latency)
+    IGT_HD void prefetch_stage(int b, int k, bool rows, bool sens, bool gains) const
+    {
+        if (k < 0 || k > P.N) return;
+#pragma unroll
+        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ[b] + k * NZ + i);
+        if (k < P.N) { w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1); }
+        if (rows) {
+            const int o = row_off(P.N, P.n_cinf, k);
+            const int n = (k == 0) ? 8 : (k == P.N ? 3 : 13);
+            for (int r = 0; r < n; r++) { w.pf(w.L.oY[b] + o + r); w.pf(w.L.oS[b] + o + r); }
+        }
+        if (sens && k < P.N) {
+#pragma unroll
+            for (int i = 0; i < NZ * NSEED; i++) w.pf(w.L.oSens + k * NZ * NSEED + i);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) w.pf(w.L.oLam + (k + 1) * NZ + i);
+        }
+        if (gains && k < P.N) {
+            w.pf(w.L.oKu + k * 2); w.pf(w.L.oKu + k * 2 + 1);
+#pragma unroll
+            for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + k * 2 * NA + i);
+        }
+    }
+
     IGT_HD void load_z(int b, int k, T *z) const
     {
 #pragma unroll
@@ -614,7 +695,8 @@ struct Solver {
             }
         }
         // slacks / multipliers, J, sum log y, theta of the initial iterate
-        T J = T(0), su = T(0), lg = T(0), th = T(0);
+        T J = T(0), su = T(0), th = T(0);
+        LogSum<T> lg;
         for (int k = 0; k <= N; k++) {
             T z[NZ], up[2], u[2] = { T(0), T(0) };
             load_z(0, k, z); load_up(0, k, up);
@@ -625,11 +707,11 @@ struct Solver {
                 T y = fmax(-c, y_min);
                 w.Y(0, o + r) = y;
                 w.S(0, o + r) = mu / y;
-                lg += log(y);
+                lg.add(y);
                 th += fabs(c + y);
             });
         }
-        Jcur = J + P.w_u * su; lgcur = lg; thetacur = th;
+        Jcur = J + P.w_u * su; lgcur = lg.total(); thetacur = th;
         return true;
     }
 
@@ -647,6 +729,7 @@ struct Solver {
             // ---- sweep 1: sensitivities
             for (int k = 0; k < N; k++) {
                 T z[NZ], u[2] = { w.U(b, k, 0), w.U(b, k, 1) }, zn[NZ], S[NZ][NSEED];
+                prefetch_stage(b, k + 1, false, false, false);
                 load_z(b, k, z);
                 rk4_step_sens(P, z, u, curv, zn, S);
 #pragma unroll
@@ -659,6 +742,7 @@ struct Solver {
             stat = T(0); rp = T(0); s_max = T(0); sy_min = T(1e30); sy_max = T(0);
             for (int k = N; k >= 0; k--) {
                 T z[NZ], up[2], u[2] = { T(0), T(0) }, gw[NW];
+                prefetch_stage(b, k - 1, true, true, false);
                 load_z(b, k, z); load_up(b, k, up);
                 if (k < N) { u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1); }
 #pragma unroll
@@ -717,6 +801,7 @@ struct Solver {
             return;
         }
         if (iters >= P.max_iter) { status = 1; done = true; return; }
+        if (iters >= P.stall_iter && rp > P.stall_rp) { status = 5; done = true; return; }   // stalled, infeasible
         while (mu > P.mu_floor &&
                fmax(fmax(stat, rp), fmax(fabs(sy_max - mu), fabs(sy_min - mu))) <= P.kappa_eps * mu)
             mu = fmax(P.mu_floor, fmin(P.kappa_mu * mu, pow(mu, P.theta_mu)));
@@ -755,6 +840,7 @@ struct Solver {
             }
             for (int k = N - 1; k >= 0; k--) {
                 T z[NZ], up[2], u[2] = { w.U(b, k, 0), w.U(b, k, 1) };
+                prefetch_stage(b, k - 1, true, true, false);
                 load_z(b, k, z); load_up(b, k, up);
                 T S[NZ][NSEED], F[NA][NW];
 #pragma unroll
@@ -860,6 +946,7 @@ struct Solver {
             for (int i = 0; i < NA; i++) dz[i] = T(0);
             for (int k = 0; k <= N; k++) {
                 T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
+                prefetch_stage(b, k + 1, true, true, true);
                 load_z(b, k, z); load_up(b, k, up);
 #pragma unroll
                 for (int i = 0; i < NA; i++) dw[i] = dz[i];
@@ -905,12 +992,14 @@ struct Solver {
         const int N = P.N, b = cur, nb = 1 - cur;
         const T tau = fmax(P.tau_min, T(1) - mu);
         T zn[NZ], upn[2] = { uprev[0], uprev[1] };
-        T J = T(0), su = T(0), lg = T(0), th = T(0);
+        T J = T(0), su = T(0), th = T(0);
+        LogSum<T> lg;
         bool fail = false;
 #pragma unroll
         for (int i = 0; i < NZ; i++) { zn[i] = x0[i]; w.Z(nb, 0, i) = zn[i]; }
         for (int k = 0; k <= N; k++) {
             T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
+            prefetch_stage(b, k + 1, true, false, true);
             load_z(b, k, z); load_up(b, k, up);
 #pragma unroll
             for (int i = 0; i < NZ; i++) dw[i] = zn[i] - z[i];
@@ -941,7 +1030,7 @@ struct Solver {
             visit_rows(P, k, zn, upn, un, ox(k), oy(k), [&](int r, T c, auto, T, auto, T, T, T, T) {
                 T yn = w.Y(nb, o + r);
                 th += fabs(c + yn);
-                lg += log(yn);
+                lg.add(yn);
             });
             J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
             if (k == N) break;
@@ -956,7 +1045,7 @@ struct Solver {
             upn[0] = un[0]; upn[1] = un[1];
         }
         trial_ok = !fail;
-        Jcand = J + P.w_u * su; lgcand = lg; thetacand = th;
+        Jcand = J + P.w_u * su; lgcand = lg.total(); thetacand = th;
     }
 
     // acceptance test (needs tcand of the candidate's terminal state when trial_ok)
@@ -1053,43 +1142,145 @@ IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, l
 }
 
 #ifdef __CUDACC__
+// Scheduler state shared by all lanes of a solve launch (device memory, zeroed / -1-filled by the
+// host before the launch).
+struct Sched {
+    unsigned long long *counter;   // next fresh problem
+    int *q_head, *q_tail;          // resume queue of donated problems (slot ids)
+    int *in_flight;                // problems fetched and not yet finished
+    int *queue;                    // [n_slots], -1 = not yet published
+    double *save_t;                // [n_slots][SAVE_T]
+    long long *save_i;             // [n_slots][SAVE_I]
+};
+constexpr int SAVE_T = 20, SAVE_I = 8;
+constexpr int DONATE_THRESH = 16;  // a warp with this many or fewer busy lanes hands its problems over
+constexpr int DONATE_MIN_ITERS = 3;
+
+template <typename T>
+__device__ __forceinline__ void save_state(const Solver<T> &sv, const Sched &sc, long slot, long p)
+{
+    double *t = sc.save_t + slot * SAVE_T;
+    long long *q = sc.save_i + slot * SAVE_I;
+    q[0] = p; q[1] = sv.cur; q[2] = sv.status; q[3] = sv.iters; q[4] = sv.ls; q[5] = sv.need_back;
+    t[0] = sv.mu; t[1] = sv.reg; t[2] = sv.alpha; t[3] = sv.Jcur; t[4] = sv.lgcur; t[5] = sv.thetacur; t[6] = sv.phi;
+    t[7] = sv.stat; t[8] = sv.rp; t[9] = sv.s_max; t[10] = sv.sy_min; t[11] = sv.sy_max;
+    t[12] = sv.tcur.V; t[13] = sv.tcur.gs; t[14] = sv.tcur.gv; t[15] = sv.tcur.Hss; t[16] = sv.tcur.Hsv; t[17] = sv.tcur.Hvv;
+}
+
+template <typename T>
+__device__ __forceinline__ long restore_state(Solver<T> &sv, const Sched &sc, long slot, const ProbIO &io)
+{
+    const double *t = sc.save_t + slot * SAVE_T;
+    const long long *q = sc.save_i + slot * SAVE_I;
+    long p = q[0];
+    sv.cur = (int)q[1]; sv.status = (int)q[2]; sv.iters = (int)q[3]; sv.ls = (int)q[4]; sv.need_back = (int)q[5];
+    sv.done = false;
+    sv.mu = T(t[0]); sv.reg = T(t[1]); sv.alpha = T(t[2]); sv.Jcur = T(t[3]); sv.lgcur = T(t[4]); sv.thetacur = T(t[5]);
+    sv.phi = T(t[6]); sv.stat = T(t[7]); sv.rp = T(t[8]); sv.s_max = T(t[9]); sv.sy_min = T(t[10]); sv.sy_max = T(t[11]);
+    sv.tcur.V = T(t[12]); sv.tcur.gs = T(t[13]); sv.tcur.gv = T(t[14]); sv.tcur.Hss = T(t[15]); sv.tcur.Hsv = T(t[16]);
+    sv.tcur.Hvv = T(t[17]);
+    sv.load_inputs(io, p, io.ctx != nullptr);
+    return p;
+}
+
 // Persistent-lane driver: every thread owns one workspace slot and keeps pulling problems from
 // a global counter until none are left.  All 32 lanes of a warp walk the phases of an iteration
 // (backward sweeps, forward trial, acceptance) together, each lane on its own problem and at
 // its own iteration count, so a slow or failing problem delays only its own lane.
+// Tail balancing: once no fresh problems remain, a warp left with <= DONATE_THRESH busy lanes
+// parks its problems (iterate in the slot's workspace, scalars in save_*) in a resume queue;
+// fully idle warps adopt up to 32 parked problems at a time, so the stragglers of many warps are
+// packed into few full warps.
 template <typename T>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
-                                                 long slot, long B, unsigned long long *counter,
+                                                 long slot, long B, const Sched &sc,
                                                  const double *guess, T *mlp_scratch, int mlp_width)
 {
     Solver<T> sv(P);
     sv.w.L.init(P.N, P.n_cinf);
     sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false;
-    long p = -1;
+    long p = -1, bound = slot;
+    int since_adopt = DONATE_MIN_ITERS;
+    // All warps of the CTA (one CTA per SM) walk the phases together -- scheduling, backward
+    // sweeps, forward trial -- separated by CTA barriers, so that the SM's instruction cache
+    // holds one phase's loop body at a time instead of eight warps' worth of different code.
     for (;;) {
+        // ---- phase 0: scheduling (fetch fresh problems, park / adopt stragglers) ----
         if (!active && !exhausted) {
-            p = (long)atomicAdd(counter, 1ULL);
+            p = (long)atomicAdd(sc.counter, 1ULL);
             if (p >= B) exhausted = true;
             else {
+                if (bound != slot) { bound = slot; sv.w.bind(ws_base, slot); }
                 const double *u_src = (io.u_init ? io.u_init : guess) + p * P.N * 2;
+                atomicAdd(sc.in_flight, 1);
                 if (sv.init(io, p, io.ctx != nullptr, u_src, io.u_init != nullptr)) {
                     sv.terminal_of(sv.cur, sv.tcur, true);
                     active = true;
                 } else {
                     sv.write_out(io, p);
+                    atomicSub(sc.in_flight, 1);
                 }
             }
         }
-        if (__all_sync(0xffffffffu, exhausted && !active)) break;
+        const bool no_new = __all_sync(FULL, exhausted);
+        int n_act = __popc(__ballot_sync(FULL, active));
+        bool wants_exit = false;
+        if (no_new) {
+            if (n_act > 0 && n_act <= DONATE_THRESH && since_adopt >= DONATE_MIN_ITERS) {
+                if (active) {                       // park: publish this lane's problem
+                    save_state(sv, sc, bound, p);
+                    __threadfence();
+                    int idx = atomicAdd(sc.q_tail, 1);
+                    atomicExch(sc.queue + idx, (int)bound);
+                    active = false;
+                }
+                n_act = 0;
+            }
+            if (n_act == 0) {
+                // adopt up to 32 parked problems; with nothing parked and nothing in flight, leave
+                int base = 0, n = 0, fl = 0;
+                if (lane == 0) {
+                    int head = *(volatile int *)sc.q_head;
+                    for (;;) {
+                        int tail = *(volatile int *)sc.q_tail;
+                        if (head >= tail) break;
+                        int want = min(32, tail - head);
+                        int old = atomicCAS(sc.q_head, head, head + want);
+                        if (old == head) { base = head; n = want; break; }
+                        head = old;
+                    }
+                    fl = *(volatile int *)sc.in_flight;
+                }
+                base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0); fl = __shfl_sync(FULL, fl, 0);
+                if (n == 0) wants_exit = (fl == 0);
+                if (lane < n) {
+                    int s_id;
+                    while ((s_id = *(volatile int *)(sc.queue + base + lane)) < 0) __nanosleep(100);
+                    __threadfence();               // also drops stale L1 lines of the adopted slot
+                    bound = s_id;
+                    sv.w.bind(ws_base, bound);
+                    p = restore_state(sv, sc, bound, io);
+                    active = true;
+                }
+                if (n > 0) since_adopt = 0;
+            }
+        }
+        if (__syncthreads_and(wants_exit)) break;
+        // ---- phase 1: backward sweeps ----
         if (active && sv.need_back) sv.backward();
+        __syncthreads();
+        // ---- phase 2: one forward trial + acceptance ----
         if (active && !sv.done) {
             sv.forward_trial();
             if (sv.trial_ok) sv.terminal_of(1 - sv.cur, sv.tcand, true);
             sv.finish_trial();
         }
-        if (active && sv.done) { sv.write_out(io, p); active = false; }
+        if (active && sv.done) { sv.write_out(io, p); active = false; atomicSub(sc.in_flight, 1); }
+        since_adopt++;
     }
 }
 #endif

@@ -98,6 +98,13 @@ class BatchSolver:
     def launches(self):
         return int(self.lib.igt_launch_count(self._h))
 
+    def measure_fma_peak(self, precision=None):
+        """TFLOP/s of dependent-free FMA chains (the solver kernels' compute roofline)."""
+        prec = self.params.precision if precision is None else {"f64": _lib.PREC_F64, "f32": _lib.PREC_F32}[precision]
+        out = C.c_double()
+        self._check(self.lib.igt_measure_fma_peak(self._h, prec, C.byref(out)), "igt_measure_fma_peak")
+        return out.value
+
     # -- value network ---------------------------------------------------------------------
     def set_mlp(self, weights, Wn, mu_f, sigma_t, mu_t):
         n = len(weights)

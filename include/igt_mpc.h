@@ -37,6 +37,7 @@ extern "C" {
 #define IGT_STATUS_X0_INFEASIBLE 2   /* x0 violates rows that involve x0 only (mpc.py:298-299,316-317 at k=0) */
 #define IGT_STATUS_REG_LIMIT 3
 #define IGT_STATUS_LINESEARCH 4
+#define IGT_STATUS_STALLED 5         /* still infeasible (|c + slack| > stall_rp) after stall_iter iterations */
 
 #define IGT_PREC_F32 0
 #define IGT_PREC_F64 1
@@ -67,6 +68,8 @@ typedef struct {
     int max_iter;      /* mpc.py:137 uses 100*N for IPOPT */
     int n_alpha;       /* step halvings per line search */
     int second_order;  /* add the dt*Hess(lambda.f) curvature term to the Riccati pass */
+    int stall_iter;    /* local-infeasibility exit: iteration >= stall_iter and ... */
+    double stall_rp;   /* ... primal residual still above stall_rp -> IGT_STATUS_STALLED */
     int precision;     /* IGT_PREC_F32 / IGT_PREC_F64: arithmetic of the solver kernels */
 } igt_params;
 
@@ -126,6 +129,10 @@ int igt_solve_host(igt_handle *h, int B, const double *x0, const double *u_prev,
 
 /* Number of kernels this library has launched on `h` so far (bench.py's gpu_launches). */
 long long igt_launch_count(const igt_handle *h);
+
+/* Measured throughput (TFLOP/s, FMA = 2 flops) of dependent-free FMA chains in `precision` on
+ * this device: the CUDA-core roofline denominator bench.py reports the solver against. */
+int igt_measure_fma_peak(igt_handle *h, int precision, double *tflops);
 
 /* Library build info: returns e.g. "igtmpc 0.1 sm_100a". */
 const char *igt_version(void);

@@ -45,7 +45,8 @@ typedef struct {
     double tau_min, reg_min, reg_up, reg_down, reg_max, eps_phi, gamma_theta, theta_small;
     int max_iter, n_alpha, second_order;
     int max_ls_fail, max_trials, predict_alpha;
-    double alpha_safety;   /* give up after this many consecutive failed line searches / total forward passes */
+    double alpha_safety;
+    int stall_iter; double stall_rp;   /* local-infeasibility exit: it >= stall_iter and |c + y|_inf > stall_rp -> status 5 */   /* give up after this many consecutive failed line searches / total forward passes */
     /* gt_mpc value term (mpc.py:326-354,:367-369; model.py:14-67); n_layers = 0 -> 'mpc' mode */
     int n_layers;
     int dims[MAX_MLP_LAYERS + 1];
@@ -474,7 +475,8 @@ static void add_dyn_hessian(const igt_oracle_params *P, const double *z, const d
 #undef ADDS
 }
 
-/* status: 0 converged, 1 iteration limit, 2 x0 infeasible, 3 regularisation limit, 4 line search */
+/* status: 0 converged, 1 iteration limit, 2 x0 infeasible, 3 regularisation limit, 4 line search,
+ * 5 stalled at an infeasible point */
 static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                      double *Zout, double *Uout, double *cost_out, double *viol_out, int *iters_out)
 {
@@ -592,6 +594,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
         }
         if (stat <= P->tol * fmax(1.0, s_max) && rp <= P->tol_rp && sy_max <= P->tol_comp) { status = 0; break; }
         if (it == P->max_iter) break;
+        if (it >= P->stall_iter && rp > P->stall_rp) { status = 5; break; }
         /* barrier update */
         while (mu > P->mu_floor &&
                fmax(fmax(stat, rp), fmax(fabs(sy_max - mu), fabs(sy_min - mu))) <= P->kappa_eps * mu)
@@ -848,6 +851,7 @@ void igt_oracle_default_options(igt_oracle_params *P)
     P->eps_phi = 1e-12; P->gamma_theta = 1e-6; P->theta_small = 1e-10;
     P->max_iter = 300; P->n_alpha = 6; P->second_order = 1;
     P->max_ls_fail = 1000; P->max_trials = 1000000; P->predict_alpha = 1; P->alpha_safety = 0.99;
+    P->stall_iter = 16; P->stall_rp = 1e-2;
 }
 
 size_t igt_oracle_params_size(void) { return sizeof(igt_oracle_params); }

@@ -47,6 +47,8 @@ class Options:
     theta_small = 1e-10
     second_order = True
     predict_alpha = True
+    stall_iter = 16
+    stall_rp = 1e-2
     alpha_safety = 0.99
 
 
@@ -212,7 +214,8 @@ def stage_cost_grad(P, z, u):
 def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Options = None,
           verbose=False):
     """Returns a Result with status (0 converged, 1 iteration limit, 2 x0 violates its own
-    rows, 3 regularisation limit in the backward pass, 4 line search failed), iters, Z[N+1,7],
+    rows, 3 regularisation limit in the backward pass, 4 line search failed, 5 stalled at an
+    infeasible point), iters, Z[N+1,7],
     U[N,2], cost, viol (max inequality-row violation in the reference's units)."""
     opt = opt or Options()
     N = P.N
@@ -292,6 +295,9 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
             res.status = 0
             break
         if it == opt.max_iter:
+            break
+        if it >= opt.stall_iter and rp > opt.stall_rp:      # stalled at an infeasible point
+            res.status = 5
             break
         # ---- barrier update (monotone, IPOPT-style) -------------------------------------
         while mu > mu_floor and max(stat, rp, abs(sy_max - mu), abs(sy_min - mu)) <= opt.kappa_eps * mu:
