@@ -220,15 +220,8 @@ def main():
     status = out["status"].cpu().numpy()
     iters = out["iters"].cpu().numpy()
     conv_per_step = int((status == 0).sum())
-    stats = torch.tensor([dev_ms, float(conv_per_step), float(iters.sum()), float(B)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, conv_all, iters_all, B_all = mx[0].item(), sm[1].item(), sm[2].item(), sm[3].item()
-    else:
-        dev_ms_max, conv_all, iters_all, B_all = dev_ms, float(conv_per_step), float(iters.sum()), float(B)
+    from igt_mpc_int_b200 import sharding
+    dev_ms_max, conv_all, iters_all, B_all = sharding.reduce_counters(dev_ms, conv_per_step, iters.sum(), B, device=dev)
     value = conv_all * args.steps / (dev_ms_max * 1e-3)
 
     # ---- end-to-end: host-pointer C ABI call with pinned host buffers ----
@@ -251,13 +244,7 @@ def main():
     torch.cuda.synchronize()
     e2e_t = time.perf_counter() - t0
     e2e_conv = int((hout_np["status"] == 0).sum())
-    e2e_stats = torch.tensor([e2e_t, float(e2e_conv)], dtype=torch.float64, device=dev)
-    if world > 1:
-        a = e2e_stats.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = e2e_stats.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        e2e_t, e2e_conv_all = a[0].item(), b[1].item()
-    else:
-        e2e_conv_all = float(e2e_conv)
+    e2e_t, e2e_conv_all, _, _ = sharding.reduce_counters(e2e_t, e2e_conv, 0, 0, device=dev)
     e2e_value = e2e_conv_all * e2e_steps / e2e_t
 
     if rank == 0:
