@@ -62,7 +62,7 @@ _lib = None
 
 EXPORTS = ("igt_version", "igt_default_params", "igt_create", "igt_destroy", "igt_last_error",
            "igt_set_mlp", "igt_rollout_dev", "igt_rollout_host", "igt_eval_host", "igt_solve_dev",
-           "igt_solve_host", "igt_launch_count", "igt_measure_fma_peak")
+           "igt_solve_host", "igt_launch_count", "igt_measure_fma_peak", "igt_mlp_value_host", "igt_set_option")
 
 
 def load():
@@ -91,6 +91,10 @@ def load():
     lib.igt_launch_count.argtypes = [vp]
     lib.igt_measure_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.igt_measure_fma_peak.restype = C.c_int
+    lib.igt_mlp_value_host.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int]
+    lib.igt_mlp_value_host.restype = C.c_int
+    lib.igt_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    lib.igt_set_option.restype = C.c_int
     lib.igt_launch_count.restype = C.c_longlong
     for f in ("igt_default_params", "igt_create", "igt_set_mlp", "igt_rollout_dev", "igt_rollout_host",
               "igt_eval_host", "igt_solve_dev", "igt_solve_host"):

@@ -18,6 +18,7 @@
 #include "../../include/igt_mpc.h"
 #include "solver_core.cuh"
 #include "params_host.hpp"
+#include "mlp_tc.cuh"
 
 using namespace igt;
 
@@ -47,14 +48,19 @@ __global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *g
     sv.compute_guess(io, p, guess + p * P.N * 2);
 }
 
-template <typename T>
+template <typename T, bool TC>
 __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws, long n_slots, long B, Sched sc,
-                                                   const double *guess, T *mlp_scratch, int mlp_width)
+                                                               const double *guess, T *mlp_scratch, int mlp_width,
+                                                               MlpTcWeights wt)
 {
+    extern __shared__ uint8_t dyn_smem[];
     long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;   // grid is sized to n_slots exactly
     const DevParams<T> &P = ConstP<T>::get();
-    solve_persistent<T>(P, io, ws, slot, B, sc, guess,
-                        mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width);
+    MlpTcCtx tc;
+    if (TC) mlp_tc_setup(tc, dyn_smem, wt);
+    solve_persistent<T, TC>(P, io, ws, slot, B, sc, guess,
+                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc);
+    if (TC) mlp_tc_teardown(tc);
 }
 
 // fp32 rollout with Kahan-compensated accumulation of the RK4 increments (x, y, s reach ~50 m
@@ -187,6 +193,39 @@ __global__ void __launch_bounds__(128) eval_kernel(long B, const double *__restr
     viol[p] = m;
 }
 
+// standalone evaluation of the gt_mpc value term (value + tangents in (s_N, v_N)) for B problems:
+// tensor-core path (one CTA = 256 problems per pass) and the fp64 CUDA-core path it is checked against
+__global__ void __launch_bounds__(256, 1) mlp_tc_kernel(MlpTcWeights wt, long B, const double *sN, const double *vN,
+                                                        const double *ctx, double *out)
+{
+    extern __shared__ uint8_t dyn_smem[];
+    MlpTcCtx c;
+    mlp_tc_setup(c, dyn_smem, wt);
+    for (long base = (long)blockIdx.x * 256; base < B; base += (long)gridDim.x * 256) {
+        long p = base + threadIdx.x;
+        bool valid = p < B;
+        float cx[4] = { 0.f, 0.f, 0.f, 0.f }, o[6];
+        float s = 0.f, v = 0.f;
+        if (valid) { s = (float)sN[p]; v = (float)vN[p]; for (int i = 0; i < 4; i++) cx[i] = (float)ctx[4 * p + i]; }
+        mlp_tc_eval(c, valid, s, v, cx, o);
+        if (valid) for (int i = 0; i < 6; i++) out[6 * p + i] = (double)o[i];
+    }
+    mlp_tc_teardown(c);
+}
+
+__global__ void __launch_bounds__(128) mlp_ref_kernel(long B, const double *sN, const double *vN, const double *ctx,
+                                                      double *out, double *scratch, int width)
+{
+    long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const DevParams<double> &P = c_Pd;
+    TermVal<double> t;
+    double cx[4] = { ctx[4 * p], ctx[4 * p + 1], ctx[4 * p + 2], ctx[4 * p + 3] };
+    double *sc = scratch + p * 12 * (long)width;
+    mlp_eval_thread(P, sN[p], vN[p], cx, sc, sc + 6 * width, width, t, true);
+    out[6 * p] = t.V; out[6 * p + 1] = t.gs; out[6 * p + 2] = t.gv; out[6 * p + 3] = t.Hss; out[6 * p + 4] = t.Hsv; out[6 * p + 5] = t.Hvv;
+}
+
 // dependent-free FMA chains: the CUDA-core roofline denominator that MEASURED_PEAKS.json lacks
 template <typename T>
 __global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters)
@@ -207,6 +246,8 @@ struct igt_handle {
     DevParams<float> Pf;
     DevParams<double> Pd;
     bool has_mlp = false;
+    MlpTcWeights tc = {};              // tensor-core copy of the value network (6-128-128-1 only)
+    int use_tc = 1;                    // igt_set_option("tensor_core_mlp", 0) forces the CUDA-core value term
     int mlp_width = 0;
     std::vector<void *> mlp_bufs;      // device weight buffers (both precisions)
     void *ws = nullptr; size_t ws_bytes = 0;
@@ -319,6 +360,48 @@ int igt_set_mlp(igt_handle *h, int n_layers, const int *dims, const double *cons
     for (int i = 0; i < 6; i++) { h->Pd.mu_f[i] = mu_f[i]; h->Pf.mu_f[i] = (float)mu_f[i]; }
     h->Pd.sigma_t = sigma_t; h->Pd.mu_t = mu_t; h->Pf.sigma_t = (float)sigma_t; h->Pf.mu_t = (float)mu_t;
     h->has_mlp = true;
+    h->tc.enabled = 0;
+    if (n_layers == 3 && dims[1] == MLP_H && dims[2] == MLP_H) {
+        // tensor-core copy: W1eff = W1 Wn, b1eff = b1 - W1eff mu_f (fp32), W2 as bf16 hi/mid/lo in UMMA core-matrix order
+        std::vector<float> w1eff(MLP_H * 6), b1eff(MLP_H), b2(MLP_H), w3(MLP_H);
+        for (int o = 0; o < MLP_H; o++) {
+            double bacc = b[0][o];
+            for (int j = 0; j < 6; j++) {
+                double acc = 0;
+                for (int i = 0; i < 6; i++) acc += W[0][o * 6 + i] * Wn[i * 6 + j];
+                w1eff[o * 6 + j] = (float)acc;
+                bacc -= acc * mu_f[j];
+            }
+            b1eff[o] = (float)bacc; b2[o] = (float)b[1][o]; w3[o] = (float)W[2][o];
+        }
+        std::vector<uint8_t> blob(3 * TC_TILE_BYTES);
+        for (int n = 0; n < MLP_H; n++)
+            for (int k = 0; k < MLP_H; k++) {
+                float x = (float)W[1][n * MLP_H + k];
+                __nv_bfloat16 hi = __float2bfloat16_rn(x);
+                float r1 = x - __bfloat162float(hi);
+                __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+                __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+                int off = tc_elem_offset(n, k);
+                memcpy(&blob[off], &hi, 2); memcpy(&blob[TC_TILE_BYTES + off], &mid, 2); memcpy(&blob[2 * TC_TILE_BYTES + off], &lo, 2);
+            }
+        void *dblob, *dw1, *db1, *db2, *dw3;
+        CK(cudaMalloc(&dblob, blob.size())); h->mlp_bufs.push_back(dblob);
+        CK(cudaMalloc(&dw1, w1eff.size() * 4)); h->mlp_bufs.push_back(dw1);
+        CK(cudaMalloc(&db1, MLP_H * 4)); h->mlp_bufs.push_back(db1);
+        CK(cudaMalloc(&db2, MLP_H * 4)); h->mlp_bufs.push_back(db2);
+        CK(cudaMalloc(&dw3, MLP_H * 4)); h->mlp_bufs.push_back(dw3);
+        CK(cudaMemcpy(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dw1, w1eff.data(), w1eff.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db1, b1eff.data(), MLP_H * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db2, b2.data(), MLP_H * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dw3, w3.data(), MLP_H * 4, cudaMemcpyHostToDevice));
+        h->tc.w2_splits = (const uint8_t *)dblob; h->tc.w1eff = (const float *)dw1; h->tc.b1eff = (const float *)db1;
+        h->tc.b2 = (const float *)db2; h->tc.w3 = (const float *)dw3;
+        h->tc.b3 = (float)b[2][0]; h->tc.sigma_t = (float)sigma_t; h->tc.mu_t = (float)mu_t;
+        h->tc.enabled = 1;
+        CK(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    }
     return IGT_OK;
 }
 
@@ -419,10 +502,22 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
         h->launches++;
     }
     int gs = (int)(n_slots / bs);
-    if (f64) solve_kernel<double><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
-                                                     nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width);
-    else solve_kernel<float><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
-                                                nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width);
+    const bool use_tc = nn_ctx && h->tc.enabled && h->use_tc;
+    if (use_tc) {
+        if (f64) {
+            CK(cudaFuncSetAttribute(solve_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            solve_kernel<double, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc);
+        } else {
+            CK(cudaFuncSetAttribute(solve_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            solve_kernel<float, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (float *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc);
+        }
+    } else if (f64) {
+        solve_kernel<double, false><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
+                                                       nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc);
+    } else {
+        solve_kernel<float, false><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
+                                                      nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width, h->tc);
+    }
     h->launches++;
     CK(cudaGetLastError());
     return IGT_OK;
@@ -530,6 +625,47 @@ int igt_measure_fma_peak(igt_handle *h, int precision, double *tflops)
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
     return IGT_OK;
+}
+
+int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN, const double *nn_ctx, double *out,
+                       int use_tensor_cores)
+{
+    if (!h) return IGT_EINVAL;
+    if (B < 0 || !sN || !vN || !nn_ctx || !out) { h->err = "igt_mlp_value: null argument"; return IGT_EINVAL; }
+    if (!h->has_mlp) { h->err = "igt_mlp_value: igt_set_mlp was never called"; return IGT_ENOMLP; }
+    if (use_tensor_cores && !h->tc.enabled) { h->err = "igt_mlp_value: tensor-core path needs a 6-128-128-1 network"; return IGT_EINVAL; }
+    if (B == 0) return IGT_OK;
+    size_t nb = (size_t)B, total = (nb * 2 + nb * 4 + nb * 6) * 8;
+    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    if (rc) return rc;
+    double *ds = (double *)h->stage, *dv = ds + nb, *dc = dv + nb, *dout = dc + nb * 4;
+    CK(cudaMemcpy(ds, sN, nb * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dv, vN, nb * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc, nn_ctx, nb * 32, cudaMemcpyHostToDevice));
+    if (use_tensor_cores) {
+        int grid = (int)((nb + 255) / 256);
+        if (grid > h->n_sm) grid = h->n_sm;
+        mlp_tc_kernel<<<grid, 256, TC_SMEM_BYTES>>>(h->tc, B, ds, dv, dc, dout);
+    } else {
+        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * nb * 8);
+        if (rc) return rc;
+        rc = upload_params(h, nullptr, false, true);
+        if (rc) return rc;
+        mlp_ref_kernel<<<(int)((nb + 127) / 128), 128>>>(B, ds, dv, dc, dout, (double *)h->mlp_scratch, h->mlp_width);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, nb * 48, cudaMemcpyDeviceToHost));
+    return IGT_OK;
+}
+
+
+int igt_set_option(igt_handle *h, const char *name, double value)
+{
+    if (!h || !name) return IGT_EINVAL;
+    if (strcmp(name, "tensor_core_mlp") == 0) { h->use_tc = value != 0.0; return IGT_OK; }
+    h->err = std::string("igt_set_option: unknown option ") + name;
+    return IGT_EINVAL;
 }
 
 }  // extern "C"

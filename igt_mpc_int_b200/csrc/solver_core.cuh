@@ -21,6 +21,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include "mlp_tc.cuh"
 
 #ifdef __CUDACC__
 #define IGT_HD __host__ __device__ __forceinline__
@@ -549,6 +550,7 @@ struct Solver {
     T stat, rp, s_max, sy_min, sy_max;
     TermVal<T> tcur, tcand;
     T Jcand, lgcand, thetacand;   // trial quantities (without the terminal value term)
+    T phi_noise = T(0);           // absolute noise floor of the merit (fp32 tensor-core value term)
     bool trial_ok;
 
     IGT_HD Solver(const DevParams<T> &P_) : P(P_) {}
@@ -1056,7 +1058,7 @@ struct Solver {
             T phin = Jcand - tcand.V - mu * lgcand;
             accepted = (phin == phin) && fabs(phin) < T(1e30) &&
                        (phin < phi - P.eps_phi * fabs(phi) || thetacand < thetacur * (T(1) - P.gamma_theta) ||
-                        (thetacand <= P.theta_small && phin <= phi + P.eps_phi * fmax(T(1), fabs(phi))));
+                        (thetacand <= P.theta_small && phin <= phi + fmax(P.eps_phi * fmax(T(1), fabs(phi)), phi_noise)));
         }
         if (accepted) {
             cur = 1 - cur;
@@ -1192,9 +1194,17 @@ __device__ __forceinline__ long restore_state(Solver<T> &sv, const Sched &sc, lo
 // fully idle warps adopt up to 32 parked problems at a time, so the stragglers of many warps are
 // packed into few full warps.
 template <typename T>
+__device__ __forceinline__ void term_from_tc(const float *o, TermVal<T> &t)
+{
+    t.V = T(o[0]); t.gs = T(o[1]); t.gv = T(o[2]); t.Hss = T(o[3]); t.Hsv = T(o[4]); t.Hvv = T(o[5]);
+}
+
+// TC = true: the gt_mpc value term of all 256 problems of the CTA is evaluated together on the
+// tensor cores (mlp_tc.cuh) at the two CTA-uniform points of the loop where it is needed.
+template <typename T, bool TC>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
                                                  long slot, long B, const Sched &sc,
-                                                 const double *guess, T *mlp_scratch, int mlp_width)
+                                                 const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc)
 {
     Solver<T> sv(P);
     sv.w.L.init(P.N, P.n_cinf);
@@ -1205,11 +1215,13 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
     bool active = false, exhausted = false;
     long p = -1, bound = slot;
     int since_adopt = DONATE_MIN_ITERS;
+    if (TC) sv.phi_noise = T(3e-7);
     // All warps of the CTA (one CTA per SM) walk the phases together -- scheduling, backward
     // sweeps, forward trial -- separated by CTA barriers, so that the SM's instruction cache
     // holds one phase's loop body at a time instead of eight warps' worth of different code.
     for (;;) {
         // ---- phase 0: scheduling (fetch fresh problems, park / adopt stragglers) ----
+        bool fresh = false;
         if (!active && !exhausted) {
             p = (long)atomicAdd(sc.counter, 1ULL);
             if (p >= B) exhausted = true;
@@ -1218,12 +1230,21 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
                 const double *u_src = (io.u_init ? io.u_init : guess) + p * P.N * 2;
                 atomicAdd(sc.in_flight, 1);
                 if (sv.init(io, p, io.ctx != nullptr, u_src, io.u_init != nullptr)) {
-                    sv.terminal_of(sv.cur, sv.tcur, true);
+                    if (!TC) sv.terminal_of(sv.cur, sv.tcur, true);
                     active = true;
+                    fresh = true;
                 } else {
                     sv.write_out(io, p);
                     atomicSub(sc.in_flight, 1);
                 }
+            }
+        }
+        if (TC) {
+            if (__syncthreads_or(fresh)) {
+                float cx[4] = { float(sv.ctx[0]), float(sv.ctx[1]), float(sv.ctx[2]), float(sv.ctx[3]) }, o[6];
+                float sN = fresh ? float(sv.w.Z(sv.cur, P.N, IS)) : 0.f, vN = fresh ? float(sv.w.Z(sv.cur, P.N, IV)) : 0.f;
+                mlp_tc_eval(*tc, fresh, sN, vN, cx, o);
+                if (fresh) term_from_tc(o, sv.tcur);
             }
         }
         const bool no_new = __all_sync(FULL, exhausted);
@@ -1274,11 +1295,20 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         if (active && sv.need_back) sv.backward();
         __syncthreads();
         // ---- phase 2: one forward trial + acceptance ----
-        if (active && !sv.done) {
-            sv.forward_trial();
-            if (sv.trial_ok) sv.terminal_of(1 - sv.cur, sv.tcand, true);
-            sv.finish_trial();
+        const bool trying = active && !sv.done;
+        if (trying) sv.forward_trial();
+        if (TC) {
+            const bool need = trying && sv.trial_ok;
+            if (__syncthreads_or(need)) {
+                float cx[4] = { float(sv.ctx[0]), float(sv.ctx[1]), float(sv.ctx[2]), float(sv.ctx[3]) }, o[6];
+                float sN = need ? float(sv.w.Z(1 - sv.cur, P.N, IS)) : 0.f, vN = need ? float(sv.w.Z(1 - sv.cur, P.N, IV)) : 0.f;
+                mlp_tc_eval(*tc, need, sN, vN, cx, o);
+                if (need) term_from_tc(o, sv.tcand);
+            }
+        } else if (trying && sv.trial_ok) {
+            sv.terminal_of(1 - sv.cur, sv.tcand, true);
         }
+        if (trying) sv.finish_trial();
         if (active && sv.done) { sv.write_out(io, p); active = false; atomicSub(sc.in_flight, 1); }
         since_adopt++;
     }

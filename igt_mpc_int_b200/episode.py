@@ -1,0 +1,158 @@
+"""Batched closed-loop episode driver: E independent two-vehicle episodes advance
+together, one batched MPC solve per 0.1 s step for all 2E vehicles.
+
+Mirrors the per-timestep glue of the reference's `evaluate.py` 'mpc' branch (evaluate.py:451-564):
+  predict            constant-acceleration forecast      common/constant_acceleration_model.py:18-82
+  share forecasts    a vehicle that solved at t-1 is forecast by its own plan   common/utils.py:339-352
+  filter_preds       obstacles behind the ego -> (-20, -20)                     common/utils.py:365-388
+  warm start         previous input sequence shifted by one                     common/utils.py:354-363
+  solve              both vehicles read forecasts made BEFORE the agent loop (Jacobi), evaluate.py:455-482
+  plant              next state = x_sol[:, 1] (perfect model), evaluate.py:491-510
+  brake fallback     a = a_min if v > 0 else 0, previous steering, one model step; v < 0 -> hold pose, v = 0
+                     evaluate.py:511-545
+  outcome            deadlock = (#vehicles with final s <= 30) >= 2, evaluate.py:566-569; collision
+                     (min centre distance < d_min) and goal (final s > 30) are derived here.
+
+The solver is any object with the BatchSolver methods `solve_batch` and `evaluate`; tests drive the
+same loop with the CPU oracle wrapped in that interface to compare outcomes.
+"""
+from dataclasses import dataclass, field
+import time
+
+import numpy as np
+
+from . import geometry as G
+
+A_MIN_BRAKE = -4.0     # mpc.yaml:8 a_min, evaluate.py:516
+V_PRED_MIN, V_PRED_MAX = -2.0, 20.0   # fourwayint.yaml:23-24 (predictor clip)
+
+
+@dataclass
+class EpisodeSpec:
+    routes: list                 # [route_0, route_1], e.g. ['13', '23']
+    s0: tuple                    # start offsets along the routes (evaluate.py:91-94, :404-418)
+
+
+@dataclass
+class EpisodeResult:
+    z_cl: np.ndarray             # [E, 2, T+1, 7] closed-loop states (x, y, s, ey, epsi, v, psi)
+    u_cl: np.ndarray             # [E, 2, T, 2]
+    solved: np.ndarray           # [E, 2, T] bool
+    deadlock: np.ndarray         # [E] bool  (evaluate.py:566-569)
+    collision: np.ndarray        # [E] bool
+    goal: np.ndarray             # [E, 2] bool
+    num_infeasible: np.ndarray   # [E, 2]
+    min_distance: np.ndarray     # [E]
+    step_latency_ms: list = field(default_factory=list)
+
+
+def reference_episode_specs(scenarios=range(1, 9), sample=0, seed=2026):
+    """All (rotation, order) variants of each scenario with the start offsets the reference draws:
+    default_rng(2026).random() * max_start in region order 1, 2, 3, 4 per sample (evaluate.py:56,
+    :91-94).  The reference picks rotation and order with an unseeded random.choice
+    (utils.py:177-179), so every variant is enumerated."""
+    max_start = (G.ROAD_LENGTH - G.ROAD_WIDTH) / 2 - (G.ROAD_WIDTH - G.CA_RADIUS)
+    rng = np.random.default_rng(seed)
+    draws = rng.random(4 * (sample + 1))[4 * sample:]
+    offs = {str(r + 1): draws[r] * max_start for r in range(4)}
+    specs = []
+    for sc in scenarios:
+        for rot in range(4):
+            for order in range(2):
+                routes = G.scenario_routes(sc, rot, order)
+                specs.append(EpisodeSpec(routes=routes, s0=tuple(offs[r[0]] for r in routes)))
+    return specs
+
+
+def _route_xy(s, route):
+    return G.frenet2global(float(s), route, exit_coord=G.EXIT_COORD.get(route))[:2]
+
+
+def _ca_step(s, v, a, dt):
+    """One constant-acceleration predictor step, constant_acceleration_model.py:69-71."""
+    return s + v * dt + 0.5 * a * dt * dt, min(max(v + a * dt, V_PRED_MIN), V_PRED_MAX)
+
+
+def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_latency=False):
+    E = len(specs)
+    B = 2 * E
+    routes = [sp.routes for sp in specs]
+    curv = np.array([G.curvature_params(r) for sp in specs for r in sp.routes])           # [B, 3]
+    z = np.zeros((B, 7))
+    for e, sp in enumerate(specs):
+        for i in range(2):
+            x, y, th = G.frenet2global(sp.s0[i], sp.routes[i])
+            if sp.routes[i] in ('32', '41'):
+                th = abs(th)                                                               # mpc.py:282-283
+            z[2 * e + i] = (x, y, sp.s0[i], 0.0, 0.0, 0.0, th)                             # evaluate.py:404-418, v0 = 0
+    u_prev = np.tile([0.1, 0.0], (B, 1))                                                   # evaluate.py:419
+    z_cl = np.zeros((E, 2, steps + 1, 7)); u_cl = np.zeros((E, 2, steps, 2))
+    solved = np.zeros((E, 2, steps), dtype=bool)
+    z_cl[:, :, 0] = z.reshape(E, 2, 7)
+    prev_x = np.zeros((B, N + 1, 7)); prev_u = np.zeros((B, N, 2)); prev_ok = np.zeros(B, dtype=bool)
+    lat = []
+    for t in range(steps):
+        # ---- forecasts of every vehicle (N+1 points: x, y, s, v) ----
+        fc = np.zeros((B, N + 1, 4))
+        for b in range(B):
+            route = routes[b // 2][b % 2]
+            if t > 0 and prev_ok[b]:
+                # V2V: the previous plan shifted by one + one constant-acceleration step (utils.py:339-352)
+                fc[b, :N, 0] = prev_x[b, 1:, 0]; fc[b, :N, 1] = prev_x[b, 1:, 1]
+                fc[b, :N, 2] = prev_x[b, 1:, 2]; fc[b, :N, 3] = prev_x[b, 1:, 5]
+                sN, vN = prev_x[b, N, 2], prev_x[b, N, 5]
+                s1, v1 = _ca_step(sN, vN, prev_u[b, N - 1, 0], dt)
+                if v1 > 5:
+                    s1, v1 = _ca_step(sN, vN, 0.0, dt)
+                fc[b, N] = (*_route_xy(s1, route), s1, v1)
+            else:
+                s, v, a = z[b, 2], z[b, 5], u_prev[b, 0]
+                fc[b, 0] = (z[b, 0], z[b, 1], s, v)
+                for k in range(N):
+                    s, v = _ca_step(s, v, a, dt)
+                    fc[b, k + 1] = (*_route_xy(s, route), s, v)
+        # ---- per-vehicle obstacle = the other vehicle's forecast, filtered (utils.py:365-388) ----
+        obs = np.zeros((B, N + 1, 2))
+        for b in range(B):
+            o = b ^ 1
+            obs[b] = G.filter_obstacle(fc[b, 0, :2], z[b, 6], fc[o, :, :2])
+        # ---- solve: warm-started vehicles and cold ones in two batched calls ----
+        t0 = time.perf_counter()
+        u_init = np.concatenate([prev_u[:, 1:], prev_u[:, -1:]], axis=1)                   # utils.py:362
+        out = dict(x=np.zeros((B, N + 1, 7)), u=np.zeros((B, N, 2)), status=np.ones(B, dtype=np.int32))
+        for mask, warm in ((prev_ok, True), (~prev_ok, False)):
+            idx = np.where(mask)[0]
+            if len(idx) == 0:
+                continue
+            r = solver.solve_batch(z[idx], u_prev[idx], curv[idx], obs[idx], u_init=u_init[idx] if warm else None)
+            out["x"][idx], out["u"][idx], out["status"][idx] = r["x"], r["u"], r["status"]
+        if record_latency:
+            lat.append(1e3 * (time.perf_counter() - t0))
+        ok = out["status"] == 0
+        # ---- plant update ----
+        z_next = z.copy(); u_app = np.zeros((B, 2))
+        z_next[ok] = out["x"][ok, 1]                                                       # evaluate.py:493
+        u_app[ok] = out["u"][ok, 0]
+        bad = np.where(~ok)[0]
+        if len(bad):
+            ub = np.zeros((len(bad), N, 2))
+            ub[:, :, 0] = np.where(z[bad, 5] > 0, A_MIN_BRAKE, 0.0)[:, None]               # evaluate.py:516
+            ub[:, :, 1] = u_prev[bad, 1][:, None]
+            roll = solver.evaluate(z[bad], u_prev[bad], curv[bad], np.full((len(bad), N + 1, 2), -20.0), ub)["x"][:, 1]
+            for j, b in enumerate(bad):
+                if z[b, 5] < 0:                                                            # evaluate.py:524-528
+                    z_next[b] = z[b]; z_next[b, 5] = 0.0
+                    u_app[b] = (0.0, u_prev[b, 1])
+                else:
+                    z_next[b] = roll[j]
+                    u_app[b] = ub[j, 0]
+        prev_x[ok], prev_u[ok] = out["x"][ok], out["u"][ok]
+        prev_ok = ok
+        z, u_prev = z_next, u_app
+        z_cl[:, :, t + 1] = z.reshape(E, 2, 7); u_cl[:, :, t] = u_app.reshape(E, 2, 2)
+        solved[:, :, t] = ok.reshape(E, 2)
+    dist = np.sqrt(np.sum((z_cl[:, 0, :, :2] - z_cl[:, 1, :, :2]) ** 2, axis=-1))
+    final_s = z_cl[:, :, -1, 2]
+    return EpisodeResult(z_cl=z_cl, u_cl=u_cl, solved=solved, deadlock=np.sum(final_s <= 30, axis=1) >= 2,
+                         collision=dist.min(axis=1) < d_min - 1e-6, goal=final_s > 30,
+                         num_infeasible=(~solved).sum(axis=2), min_distance=dist.min(axis=1), step_latency_ms=lat)

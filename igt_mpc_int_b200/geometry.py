@@ -23,6 +23,15 @@ RIGHT = ('14', '21', '32', '43')
 STRAIGHT = ('13', '24', '31', '42')
 ROUTES = LEFT + RIGHT + STRAIGHT
 
+# Exit-lane coordinate the reference's frenet2global returns after the arc: it reads the last
+# sample of its generated reference track (`ref['x'][-1]` / `ref['y'][-1]`, utils.py:558), which is
+# a few millimetres off the nominal lane centre.  Values captured by running the reference's
+# ReferenceGenerator (tests/golden/geometry.npz pins them).
+EXIT_COORD = {
+    '12': 27.89571278670408, '23': 2.8042872132959236, '34': 22.10428721329592, '41': 8.595712786704077,
+    '14': 22.099438308054523, '21': 8.600561691945474, '32': 27.90056169194547, '43': 2.7994383080545244,
+}
+
 # scenario route-pair sets, common/utils.py:142-149
 SCENARIOS = {
     1: [('13', '23'), ('24', '34'), ('31', '41'), ('42', '12')],

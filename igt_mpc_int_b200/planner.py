@@ -120,6 +120,18 @@ class BatchSolver:
         self._check(rc, "igt_set_mlp")
         self.has_mlp = True
 
+    def set_option(self, name, value):
+        self._check(self.lib.igt_set_option(self._h, name.encode(), float(value)), "igt_set_option")
+
+    def mlp_value(self, sN, vN, nn_ctx, tensor_cores=True):
+        """Value term and its (s_N, v_N) derivatives: out[B,6] = (V, Vs, Vv, Vss, Vsv, Vvv)."""
+        sN = _f64(sN).ravel(); B = sN.shape[0]
+        vN = _f64(vN, (B,)); nn_ctx = _f64(nn_ctx, (B, 4))
+        out = np.empty((B, 6))
+        rc = self.lib.igt_mlp_value_host(self._h, B, _hp(sN), _hp(vN), _hp(nn_ctx), _hp(out), 1 if tensor_cores else 0)
+        self._check(rc, "igt_mlp_value_host")
+        return out
+
     # -- host-pointer calls (copies inside) ---------------------------------------------------
     def solve_batch(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None, out=None):
         """numpy in / numpy out.  Returns dict(x[B,N+1,7], u[B,N,2], cost, viol, status, iters)."""

@@ -130,6 +130,16 @@ int igt_solve_host(igt_handle *h, int B, const double *x0, const double *u_prev,
 /* Number of kernels this library has launched on `h` so far (bench.py's gpu_launches). */
 long long igt_launch_count(const igt_handle *h);
 
+/* The gt_mpc value term alone (mpc.py:367-369, model.py:53-67): V(W (x_N - mu_f)) sigma_t + mu_t and its
+ * first / second derivatives in (s_N, v_N), out[B,6] = (V, dV/ds, dV/dv, d2V/dss, d2V/dsv, d2V/dvv).
+ * use_tensor_cores = 1: tcgen05 kernel (6-128-128-1 networks); 0: fp64 CUDA-core kernel.  Host fp64 arrays. */
+int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN, const double *nn_ctx,
+                       double *out, int use_tensor_cores);
+
+/* Run-time switches.  "tensor_core_mlp" (default 1): evaluate the gt_mpc value term of 6-128-128-1 networks
+ * with the tcgen05 kernel inside the solver; 0 = fp64 CUDA-core evaluation (always used for other shapes). */
+int igt_set_option(igt_handle *h, const char *name, double value);
+
 /* Measured throughput (TFLOP/s, FMA = 2 flops) of dependent-free FMA chains in `precision` on
  * this device: the CUDA-core roofline denominator bench.py reports the solver against. */
 int igt_measure_fma_peak(igt_handle *h, int precision, double *tflops);
