@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *g
 template <typename T, bool TC>
 __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws, long n_slots, long B, Sched sc,
                                                                const double *guess, T *mlp_scratch, int mlp_width,
-                                                               MlpTcWeights wt)
+                                                               MlpTcWeights wt, int quota)
 {
     extern __shared__ uint8_t dyn_smem[];
     long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;   // grid is sized to n_slots exactly
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws,
     MlpTcCtx tc;
     if (TC) mlp_tc_setup(tc, dyn_smem, wt);
     solve_persistent<T, TC>(P, io, ws, slot, B, sc, guess,
-                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc);
+                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc, quota);
     if (TC) mlp_tc_teardown(tc);
 }
 
@@ -468,11 +468,16 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     const bool f64 = h->prm.precision == IGT_PREC_F64;
     WsLayout L; L.init(h->prm.N, h->prm.n_cinf);
     size_t esz = f64 ? 8 : 4;
-    // persistent lanes: at most SLOTS_PER_SM threads per SM, never more than problems
+    // persistent lanes: one CTA of SOLVE_BLOCK threads per SM.  A batch smaller than the machine is spread
+    // over all SMs, a whole number of warps each: `quota` threads per CTA fetch problems, the rest of
+    // the CTA only helps in the CTA-wide phases (and adopts stragglers in the tail).
     const int bs = SOLVE_BLOCK;
-    long max_slots = (long)h->n_sm * SLOTS_PER_SM;
-    long n_slots = ((B + bs - 1) / bs) * (long)bs;
-    if (n_slots > max_slots) n_slots = max_slots;
+    long n_cta = ((long)B + 31) / 32;
+    if (n_cta > h->n_sm) n_cta = h->n_sm;
+    long per_cta = ((long)B + n_cta - 1) / n_cta;
+    int quota = (int)((per_cta + 31) / 32 * 32);
+    if (quota > bs) quota = bs;
+    long n_slots = n_cta * bs;
     int rc = grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * n_slots * esz);
     if (rc) return rc;
     if (nn_ctx) {
@@ -506,17 +511,17 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     if (use_tc) {
         if (f64) {
             CK(cudaFuncSetAttribute(solve_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-            solve_kernel<double, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc);
+            solve_kernel<double, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota);
         } else {
             CK(cudaFuncSetAttribute(solve_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-            solve_kernel<float, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (float *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc);
+            solve_kernel<float, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (float *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota);
         }
     } else if (f64) {
         solve_kernel<double, false><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
-                                                       nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc);
+                                                       nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota);
     } else {
         solve_kernel<float, false><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
-                                                      nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width, h->tc);
+                                                      nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota);
     }
     h->launches++;
     CK(cudaGetLastError());

@@ -532,6 +532,20 @@ IGT_HD void add_dyn_hessian(const DevParams<T> &P, const T *z, T df, const T *cu
     H[sym11(IUD, IUD)] += dt * v * (G_bb * b1 * b1 + G_b * b2);
 }
 
+// sweep 1 of one stage: sensitivities S_k of z_{k+1} w.r.t. the 6 seeds, from (z_k, u_k) of buffer b
+template <typename T>
+IGT_HD void sens_stage(const DevParams<T> &P, const Ws<T> &w, int b, int k, const T *curv)
+{
+    T z[NZ], u[2] = { w.U(b, k, 0), w.U(b, k, 1) }, zn[NZ], S[NZ][NSEED];
+#pragma unroll
+    for (int i = 0; i < NZ; i++) z[i] = w.Z(b, k, i);
+    rk4_step_sens(P, z, u, curv, zn, S);
+#pragma unroll
+    for (int i = 0; i < NZ; i++)
+#pragma unroll
+        for (int j = 0; j < NSEED; j++) w.Sens(k, i, j) = S[i][j];
+}
+
 // ------------------------------------------------------------------ the solver ---------
 template <typename T>
 struct Solver {
@@ -552,6 +566,7 @@ struct Solver {
     T Jcand, lgcand, thetacand;   // trial quantities (without the terminal value term)
     T phi_noise = T(0);           // absolute noise floor of the merit (fp32 tensor-core value term)
     bool trial_ok;
+    bool sens_external = false;   // sweep 1 is done outside backward() (CTA-wide phase in the kernels)
 
     IGT_HD Solver(const DevParams<T> &P_) : P(P_) {}
 
@@ -728,17 +743,9 @@ struct Solver {
     {
         const int N = P.N, b = cur;
         if (need_back == 2) {
-            // ---- sweep 1: sensitivities
-            for (int k = 0; k < N; k++) {
-                T z[NZ], u[2] = { w.U(b, k, 0), w.U(b, k, 1) }, zn[NZ], S[NZ][NSEED];
-                prefetch_stage(b, k + 1, false, false, false);
-                load_z(b, k, z);
-                rk4_step_sens(P, z, u, curv, zn, S);
-#pragma unroll
-                for (int i = 0; i < NZ; i++)
-#pragma unroll
-                    for (int j = 0; j < NSEED; j++) w.Sens(k, i, j) = S[i][j];
-            }
+            // ---- sweep 1: sensitivities (the kernels run it CTA-wide instead, see sens_phase_cta)
+            if (!sens_external)
+                for (int k = 0; k < N; k++) sens_stage(P, w, b, k, curv);
             // ---- sweep 2: adjoint + residuals
             T lam[NA];
             stat = T(0); rp = T(0); s_max = T(0); sy_min = T(1e30); sy_max = T(0);
@@ -1201,18 +1208,62 @@ __device__ __forceinline__ void term_from_tc(const float *o, TermVal<T> &t)
 
 // TC = true: the gt_mpc value term of all 256 problems of the CTA is evaluated together on the
 // tensor cores (mlp_tc.cuh) at the two CTA-uniform points of the loop where it is needed.
+// CTA-wide sweep 1.  The sensitivities of a stage depend only on that stage's (z_k, u_k), so the
+// (problem, stage) pairs of every problem of the CTA that needs a full backward pass are independent
+// work items; they are dealt out over all threads of the CTA.  Every lane is busy whatever the
+// mix of per-problem states, a lone straggler gets its N stages done by N threads at once, and the
+// loop body (one RK4 step with tangents) is small enough to stay in the instruction cache.
+constexpr int MAX_SOLVE_BLOCK = 256;
+template <typename T>
+__device__ __forceinline__ void sens_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
+                                               long bound, int cur, const T *curv)
+{
+    __shared__ int s_wcnt[MAX_SOLVE_BLOCK / 32];
+    __shared__ int s_slot[MAX_SOLVE_BLOCK];
+    __shared__ int s_cur[MAX_SOLVE_BLOCK];
+    __shared__ T s_curv[3][MAX_SOLVE_BLOCK];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const unsigned m = __ballot_sync(FULL, need);
+    if (lane == 0) s_wcnt[warp] = __popc(m);
+    __syncthreads();
+    int base = 0, n = 0;
+    for (int i = 0; i < nw; i++) { int c = s_wcnt[i]; if (i < warp) base += c; n += c; }
+    if (need) {
+        const int idx = base + __popc(m & ((1u << lane) - 1u));
+        s_slot[idx] = (int)bound; s_cur[idx] = cur;
+        s_curv[0][idx] = curv[0]; s_curv[1][idx] = curv[1]; s_curv[2][idx] = curv[2];
+    }
+    __syncthreads();
+    if (n > 0) {
+        Ws<T> w; w.L = L;
+        const int total = n * P.N;
+        for (int it = tid; it < total; it += blockDim.x) {
+            const int j = it % n, k = it / n;
+            w.bind(ws_base, s_slot[j]);
+            const T cv[3] = { s_curv[0][j], s_curv[1][j], s_curv[2][j] };
+            sens_stage(P, w, s_cur[j], k, cv);
+        }
+    }
+    __syncthreads();
+}
+
 template <typename T, bool TC>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
                                                  long slot, long B, const Sched &sc,
-                                                 const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc)
+                                                 const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc,
+                                                 int quota)
 {
     Solver<T> sv(P);
     sv.w.L.init(P.N, P.n_cinf);
     sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
+    sv.sens_external = true;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    bool active = false, exhausted = false;
+    // only the first `quota` threads of a CTA fetch fresh problems, so that a batch smaller than the
+    // machine is spread over all SMs; the other threads still work in the CTA-wide phases
+    bool active = false, exhausted = (int)threadIdx.x >= quota;
     long p = -1, bound = slot;
     int since_adopt = DONATE_MIN_ITERS;
     if (TC) sv.phi_noise = T(3e-7);
@@ -1291,7 +1342,9 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
             }
         }
         if (__syncthreads_and(wants_exit)) break;
-        // ---- phase 1: backward sweeps ----
+        // ---- phase 1a: sensitivities, CTA-wide ----
+        sens_phase_cta(P, ws_base, sv.w.L, active && sv.need_back == 2, bound, sv.cur, sv.curv);
+        // ---- phase 1b: adjoint, Riccati, step bound (per problem) ----
         if (active && sv.need_back) sv.backward();
         __syncthreads();
         // ---- phase 2: one forward trial + acceptance ----
