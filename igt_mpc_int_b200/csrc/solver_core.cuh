@@ -36,6 +36,10 @@ namespace igt {
 constexpr int NZ = 7, NA = 9, NW = 11, NSEED = 6;
 enum { IX = 0, IY, IS, IEY, IEPSI, IV, IPSI, IPA, IPD, IUA, IUD };
 constexpr int MAX_CINF = 128;
+// Node-local summaries of the inequality rows.  The rows of a node touch 8 entries of the gradient in
+// w = (zeta, u) and, together with the dynamics second-order term, 22 entries of the symmetric
+// w-space Hessian; these are what the sequential sweeps need from a node.
+constexpr int NGE = 8, NHE = 22;
 constexpr int MAX_MLP_LAYERS = 5;
 constexpr int N_GUESS = 5;
 
@@ -67,7 +71,7 @@ IGT_HD int row_total(int N, int n_cinf) { return row_off(N, n_cinf, N) + 3; }
 
 struct WsLayout {
     int N, M;
-    int oZ[2], oU[2], oY[2], oS[2], oSens, oLam, oKu, oKK, total;
+    int oZ[2], oU[2], oY[2], oS[2], oSens, oLam, oKu, oKK, oGw, oRed, oGl, oHl, oTr, oDu, total;
     IGT_HD void init(int N_, int n_cinf)
     {
         N = N_;
@@ -81,6 +85,12 @@ struct WsLayout {
         oLam = o;  o += NZ * (N + 1);
         oKu = o;   o += 2 * N;
         oKK = o;   o += 2 * NA * N;
+        oGw = o;   o += NGE * (N + 1);     // node-local row summaries, see node_phase1 / node_phase2
+        oRed = o;  o += 4 * (N + 1);
+        oGl = o;   o += NGE * (N + 1);
+        oHl = o;   o += NHE * (N + 1);
+        oTr = o;   o += 3 * (N + 1);       // per-node results of a trial step, see node_phase3
+        oDu = o;   o += 2 * N;             // control change of the trial step (exact, not new - old)
         total = o;
     }
 };
@@ -109,6 +119,12 @@ struct Ws {
     IGT_HD T &Lam(int k, int i) const { return at(L.oLam + k * NZ + i); }
     IGT_HD T &ku(int k, int i) const { return at(L.oKu + k * 2 + i); }
     IGT_HD T &KK(int k, int i, int j) const { return at(L.oKK + (k * 2 + i) * NA + j); }
+    IGT_HD T &Gw(int k, int e) const { return at(L.oGw + k * NGE + e); }
+    IGT_HD T &Red(int k, int e) const { return at(L.oRed + k * 4 + e); }
+    IGT_HD T &Gl(int k, int e) const { return at(L.oGl + k * NGE + e); }
+    IGT_HD T &Hl(int k, int e) const { return at(L.oHl + k * NHE + e); }
+    IGT_HD T &Tr(int k, int e) const { return at(L.oTr + k * 3 + e); }
+    IGT_HD T &Du(int k, int i) const { return at(L.oDu + k * 2 + i); }
 };
 
 // problem inputs / outputs: batch-major AoS arrays exactly as the C ABI receives them
@@ -158,9 +174,14 @@ IGT_HD void rot_small(double, double sa, double ca, double d, double *s, double 
         *s = sa * cd + ca * sd; *c = ca * cd - sa * sd;
         return;
     }
-    double d2 = d * d;
-    double sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880 + d2 * (-1.0 / 39916800 + d2 * (1.0 / 6227020800.0 + d2 * (-1.0 / 1307674368000.0))))))));
-    double cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320 + d2 * (-1.0 / 3628800 + d2 * (1.0 / 479001600.0 + d2 * (-1.0 / 87178291200.0)))))));
+    double d2 = d * d, sd, cd;
+    if (fabs(d) <= 0.0625) {     // the usual case (drift within one 0.1 s step): d^13 / 13! < 4e-26
+        sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880 + d2 * (-1.0 / 39916800))))));
+        cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320 + d2 * (-1.0 / 3628800)))));
+    } else {
+        sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880 + d2 * (-1.0 / 39916800 + d2 * (1.0 / 6227020800.0 + d2 * (-1.0 / 1307674368000.0))))))));
+        cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320 + d2 * (-1.0 / 3628800 + d2 * (1.0 / 479001600.0 + d2 * (-1.0 / 87178291200.0)))))));
+    }
     *s = sa * cd + ca * sd;
     *c = ca * cd - sa * sd;
 }
@@ -189,7 +210,7 @@ IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const
     T c1, s1, cp, sp;
     rot_small(ab.a1, ab.s1b, ab.c1b, epsi - ab.e0, &s1, &c1);
     rot_small(ab.a2, ab.spb, ab.cpb, psi - ab.p0, &sp, &cp);
-    T iden = T(1) / (T(1) - K * ey);
+    T iden = (K == T(0)) ? T(1) : T(1) / (T(1) - K * ey);     // straight segments: no division
     T sdot = v * c1 * iden;
     T yaw = v * sl.sb * P.inv_lr;
     zd[IS] = sdot;
@@ -532,18 +553,167 @@ IGT_HD void add_dyn_hessian(const DevParams<T> &P, const T *z, T df, const T *cu
     H[sym11(IUD, IUD)] += dt * v * (G_bb * b1 * b1 + G_b * b2);
 }
 
-// sweep 1 of one stage: sensitivities S_k of z_{k+1} w.r.t. the 6 seeds, from (z_k, u_k) of buffer b
-template <typename T>
-IGT_HD void sens_stage(const DevParams<T> &P, const Ws<T> &w, int b, int k, const T *curv)
+// gradient entries / Hessian entries kept per node (compile-time tables as functions so that every
+// use indexes registers statically after unrolling)
+IGT_HD constexpr int ge_idx(int e)
 {
-    T z[NZ], u[2] = { w.U(b, k, 0), w.U(b, k, 1) }, zn[NZ], S[NZ][NSEED];
+    return e == 0 ? IV : e == 1 ? IEY : e == 2 ? IX : e == 3 ? IY : e == 4 ? IUA : e == 5 ? IUD : e == 6 ? IPA : IPD;
+}
+IGT_HD constexpr int he_i(int e)
+{
+    return e == 0 ? IV : e == 1 ? IEY : e == 2 ? IX : e == 3 ? IX : e == 4 ? IY : e == 5 ? IUA : e == 6 ? IUD
+         : e == 7 ? IPA : e == 8 ? IPA : e == 9 ? IPD : e == 10 ? IPD : e == 11 ? IV
+         : e == 12 ? IEY : e == 13 ? IEPSI : e == 14 ? IPSI : e == 15 ? IEY : e == 16 ? IEPSI : e == 17 ? IV
+         : e == 18 ? IEY : e == 19 ? IEPSI : e == 20 ? IPSI : IV;
+}
+IGT_HD constexpr int he_j(int e)
+{
+    return e == 0 ? IV : e == 1 ? IEY : e == 2 ? IX : e == 3 ? IY : e == 4 ? IY : e == 5 ? IUA : e == 6 ? IUD
+         : e == 7 ? IPA : e == 8 ? IUA : e == 9 ? IPD : e == 10 ? IUD : e == 11 ? IUA
+         : e == 12 ? IEPSI : e == 13 ? IEPSI : e == 14 ? IPSI : e == 15 ? IV : e == 16 ? IV : e == 17 ? IPSI
+         : e == 18 ? IUD : e == 19 ? IUD : e == 20 ? IUD : IUD;
+}
+
+// what a node phase needs to know about the problem it works for
+template <typename T>
+struct NodeCtx {
+    T curv[3], uprev[2], mu, alpha;
+    const double *obs;
+    int cur, second_order;
+};
+
+template <typename T>
+IGT_HD void node_load(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k, T *z, T *up, T *u)
+{
+    const int b = c.cur;
 #pragma unroll
     for (int i = 0; i < NZ; i++) z[i] = w.Z(b, k, i);
-    rk4_step_sens(P, z, u, curv, zn, S);
+    if (k == 0) { up[0] = c.uprev[0]; up[1] = c.uprev[1]; }
+    else { up[0] = w.U(b, k - 1, 0); up[1] = w.U(b, k - 1, 1); }
+    if (k < P.N) { u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1); } else { u[0] = u[1] = T(0); }
+}
+
+// Node phase 1 (independent of the barrier parameter and of the adjoint): sensitivities of stage k
+// and the row summaries the adjoint sweep needs -- sum of g * s per gradient entry, and the node's
+// share of the residual norms (primal residual, largest multiplier, min / max of s * y).
+template <typename T>
+IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k)
+{
+    const int N = P.N, b = c.cur;
+    T z[NZ], up[2], u[2];
+    node_load(P, w, c, k, z, up, u);
+    if (k < N) {
+        T zn[NZ], S[NZ][NSEED];
+        rk4_step_sens(P, z, u, c.curv, zn, S);
 #pragma unroll
-    for (int i = 0; i < NZ; i++)
+        for (int i = 0; i < NZ; i++)
 #pragma unroll
-        for (int j = 0; j < NSEED; j++) w.Sens(k, i, j) = S[i][j];
+            for (int j = 0; j < NSEED; j++) w.Sens(k, i, j) = S[i][j];
+    }
+    T gw[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i++) gw[i] = T(0);
+    T rp = T(0), s_max = T(0), sy_min = T(1e30), sy_max = T(0);
+    const int o = row_off(N, P.n_cinf, k);
+    visit_rows(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
+        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        T s = w.S(b, o + r), y = w.Y(b, o + r);
+        gw[i0] += g0 * s;
+        if constexpr (i1 >= 0) gw[i1] += g1 * s;
+        rp = fmax(rp, fabs(cv + y));
+        s_max = fmax(s_max, s);
+        T sy = s * y;
+        sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
+    });
+#pragma unroll
+    for (int e = 0; e < NGE; e++) w.Gw(k, e) = gw[ge_idx(e)];
+    w.Red(k, 0) = rp; w.Red(k, 1) = s_max; w.Red(k, 2) = sy_min; w.Red(k, 3) = sy_max;
+}
+
+// Node phase 2 (after the barrier update and the adjoint sweep): the rows' share of the perturbed
+// KKT system of node k -- gradient sum of g * (s + (s c + mu) / y), Hessian sum of (s / y) g g' plus
+// s * Hess(c) for the collision row -- and the dynamics second-order term dt * Hess(lambda_{k+1} . f).
+template <typename T>
+IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k)
+{
+    const int N = P.N, b = c.cur;
+    const T mu = c.mu;
+    T z[NZ], up[2], u[2];
+    node_load(P, w, c, k, z, up, u);
+    T g[NW], H[66];
+#pragma unroll
+    for (int i = 0; i < NW; i++) g[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < 66; i++) H[i] = T(0);
+    if (k < N && c.second_order) {
+        T ln[NZ];
+#pragma unroll
+        for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
+        add_dyn_hessian(P, z, u[1], c.curv, ln, H);
+    }
+    const int o = row_off(N, P.n_cinf, k);
+    visit_rows(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](int r, T cv, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
+        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        T s = w.S(b, o + r), y = w.Y(b, o + r);
+        T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
+        g[i0] += g0 * gr;
+        H[sym11(i0, i0)] += sig * g0 * g0;
+        if constexpr (i1 >= 0) {
+            g[i1] += g1 * gr;
+            H[sym11(i1, i1)] += sig * g1 * g1;
+            H[sym11(i0, i1)] += sig * g0 * g1;
+        }
+        if constexpr (i0 == IX) {
+            H[sym11(IX, IX)] += s * hxx; H[sym11(IX, IY)] += s * hxy; H[sym11(IY, IY)] += s * hyy;
+        }
+    });
+#pragma unroll
+    for (int e = 0; e < NGE; e++) w.Gl(k, e) = g[ge_idx(e)];
+#pragma unroll
+    for (int e = 0; e < NHE; e++) w.Hl(k, e) = H[sym11(he_i(e), he_j(e))];
+}
+
+// Node phase 3 (after the closed-loop rollout of a trial step): slack / multiplier update of the
+// rows of node k along the step actually taken (d w_k = new - old iterate), the fraction-to-boundary
+// test, and the node's share of the infeasibility and of the barrier sum at the new point.
+// Tr(k, .) = (sum |c + y|, sum log y, 1 if the boundary rule failed).
+template <typename T>
+IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k)
+{
+    const int N = P.N, b = c.cur, nb = 1 - c.cur;
+    const T mu = c.mu, alpha = c.alpha, tau = fmax(P.tau_min, T(1) - mu);
+    T z[NZ], up[2], u[2], zn[NZ], upn[2], un[2], dw[NW];
+    node_load(P, w, c, k, z, up, u);
+#pragma unroll
+    for (int i = 0; i < NZ; i++) { zn[i] = w.Z(nb, k, i); dw[i] = zn[i] - z[i]; }
+    if (k == 0) { upn[0] = c.uprev[0]; upn[1] = c.uprev[1]; }
+    else { upn[0] = w.U(nb, k - 1, 0); upn[1] = w.U(nb, k - 1, 1); }
+    if (k < N) { un[0] = w.U(nb, k, 0); un[1] = w.U(nb, k, 1); } else { un[0] = un[1] = T(0); }
+    dw[IPA] = upn[0] - up[0]; dw[IPD] = upn[1] - up[1];
+    if (k < N) { dw[IUA] = w.Du(k, 0); dw[IUD] = w.Du(k, 1); } else { dw[IUA] = dw[IUD] = T(0); }
+    const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]);
+    const int o = row_off(N, P.n_cinf, k);
+    bool fail = false;
+    visit_rows(P, k, z, up, u, ox, oy, [&](int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
+        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        T s = w.S(b, o + r), y = w.Y(b, o + r);
+        T dc = g0 * dw[i0];
+        if constexpr (i1 >= 0) dc += g1 * dw[i1];
+        T yn = y - alpha * (cv + y) - dc;
+        T sn = s + (alpha * (s * cv + mu) + s * dc) / y;
+        if (yn < (T(1) - tau) * y) fail = true;                 // fraction to the boundary
+        sn = fmax(sn, (T(1) - tau) * s);                        // multiplier safeguard
+        w.Y(nb, o + r) = yn; w.S(nb, o + r) = sn;
+    });
+    T th = T(0);
+    LogSum<T> lg;
+    if (!fail)
+        visit_rows(P, k, zn, upn, un, ox, oy, [&](int r, T cv, auto, T, auto, T, T, T, T) {
+            T yn = w.Y(nb, o + r);
+            th += fabs(cv + yn);
+            lg.add(yn);
+        });
+    w.Tr(k, 0) = th; w.Tr(k, 1) = fail ? T(0) : lg.total(); w.Tr(k, 2) = fail ? T(1) : T(0);
 }
 
 // ------------------------------------------------------------------ the solver ---------
@@ -566,7 +736,6 @@ struct Solver {
     T Jcand, lgcand, thetacand;   // trial quantities (without the terminal value term)
     T phi_noise = T(0);           // absolute noise floor of the merit (fp32 tensor-core value term)
     bool trial_ok;
-    bool sens_external = false;   // sweep 1 is done outside backward() (CTA-wide phase in the kernels)
 
     IGT_HD Solver(const DevParams<T> &P_) : P(P_) {}
 
@@ -606,6 +775,27 @@ struct Solver {
             w.pf(w.L.oKu + k * 2); w.pf(w.L.oKu + k * 2 + 1);
 #pragma unroll
             for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + k * 2 * NA + i);
+        }
+    }
+
+    // next stage of the backward sweeps: sensitivities, node summaries, the few iterate entries used
+    IGT_HD void prefetch_back(int b, int k, bool riccati) const
+    {
+        if (k < 0) return;
+#pragma unroll
+        for (int i = 0; i < NZ * NSEED; i++) w.pf(w.L.oSens + k * NZ * NSEED + i);
+        w.pf(w.L.oZ[b] + k * NZ + IEY); w.pf(w.L.oZ[b] + k * NZ + IEPSI);
+        w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1);
+        if (riccati) {
+#pragma unroll
+            for (int e = 0; e < NGE; e++) w.pf(w.L.oGl + k * NGE + e);
+#pragma unroll
+            for (int e = 0; e < NHE; e++) w.pf(w.L.oHl + k * NHE + e);
+        } else {
+#pragma unroll
+            for (int e = 0; e < NGE; e++) w.pf(w.L.oGw + k * NGE + e);
+#pragma unroll
+            for (int e = 0; e < 4; e++) w.pf(w.L.oRed + k * 4 + e);
         }
     }
 
@@ -738,73 +928,70 @@ struct Solver {
         terminal_value(w.Z(b, P.N, IS), w.Z(b, P.N, IV), t, want_deriv);
     }
 
-    // sweeps 1-3.  Sets done/status on convergence or failure.
-    IGT_HD void backward()
+    IGT_HD NodeCtx<T> node_ctx() const
+    {
+        NodeCtx<T> c;
+        c.curv[0] = curv[0]; c.curv[1] = curv[1]; c.curv[2] = curv[2];
+        c.uprev[0] = uprev[0]; c.uprev[1] = uprev[1];
+        c.mu = mu; c.alpha = alpha; c.obs = obs; c.cur = cur; c.second_order = P.second_order;
+        return c;
+    }
+
+    // sweep 2: adjoint recursion and KKT residuals from the node summaries of node_phase1
+    IGT_HD void adjoint_sweep()
     {
         const int N = P.N, b = cur;
-        if (need_back == 2) {
-            // ---- sweep 1: sensitivities (the kernels run it CTA-wide instead, see sens_phase_cta)
-            if (!sens_external)
-                for (int k = 0; k < N; k++) sens_stage(P, w, b, k, curv);
-            // ---- sweep 2: adjoint + residuals
-            T lam[NA];
-            stat = T(0); rp = T(0); s_max = T(0); sy_min = T(1e30); sy_max = T(0);
-            for (int k = N; k >= 0; k--) {
-                T z[NZ], up[2], u[2] = { T(0), T(0) }, gw[NW];
-                prefetch_stage(b, k - 1, true, true, false);
-                load_z(b, k, z); load_up(b, k, up);
-                if (k < N) { u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1); }
+        T lam[NA];
+        stat = T(0); rp = T(0); s_max = T(0); sy_min = T(1e30); sy_max = T(0);
+        for (int k = N; k >= 0; k--) {
+            T gw[NW];
+            prefetch_back(b, k - 1, false);
 #pragma unroll
-                for (int i = 0; i < NW; i++) gw[i] = T(0);
-                int o = row_off(N, P.n_cinf, k);
-                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
-                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-                    T s = w.S(b, o + r), y = w.Y(b, o + r);
-                    gw[i0] += g0 * s;
-                    if constexpr (i1 >= 0) gw[i1] += g1 * s;
-                    rp = fmax(rp, fabs(c + y));
-                    s_max = fmax(s_max, s);
-                    T sy = s * y;
-                    sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
-                });
-                if (k == N) {
+            for (int i = 0; i < NW; i++) gw[i] = T(0);
 #pragma unroll
-                    for (int i = 0; i < NA; i++) lam[i] = gw[i];
-                    lam[IEY] += T(2) * z[IEY]; lam[IEPSI] += T(2) * z[IEPSI];
-                    lam[IS] -= tcur.gs; lam[IV] -= tcur.gv;
-                } else {
-                    T S[NZ][NSEED], F[NA][NW];
+            for (int e = 0; e < NGE; e++) gw[ge_idx(e)] = w.Gw(k, e);
+            rp = fmax(rp, w.Red(k, 0)); s_max = fmax(s_max, w.Red(k, 1));
+            sy_min = fmin(sy_min, w.Red(k, 2)); sy_max = fmax(sy_max, w.Red(k, 3));
+            const T ey = w.Z(b, k, IEY), epsi = w.Z(b, k, IEPSI);
+            if (k == N) {
 #pragma unroll
-                    for (int i = 0; i < NZ; i++)
+                for (int i = 0; i < NA; i++) lam[i] = gw[i];
+                lam[IS] -= tcur.gs; lam[IV] -= tcur.gv;
+            } else {
+                T S[NZ][NSEED], F[NA][NW];
 #pragma unroll
-                        for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
-                    build_F(P, S, F);
-                    T ln[NA];
+                for (int i = 0; i < NZ; i++)
 #pragma unroll
-                    for (int i = 0; i < NA; i++) ln[i] = lam[i];
+                    for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
+                build_F(P, S, F);
+                T ln[NA];
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        T gu = T(2) * P.w_u * u[j] + gw[NA + j];
+                for (int i = 0; i < NA; i++) ln[i] = lam[i];
 #pragma unroll
-                        for (int a = 0; a < NA; a++) if (fmask(a, NA + j)) gu += F[a][NA + j] * ln[a];
-                        stat = fmax(stat, fabs(gu));
-                    }
+                for (int j = 0; j < 2; j++) {
+                    T gu = T(2) * P.w_u * w.U(b, k, j) + gw[NA + j];
 #pragma unroll
-                    for (int i = 0; i < NA; i++) {
-                        T acc = gw[i];
-#pragma unroll
-                        for (int a = 0; a < NA; a++) if (fmask(a, i)) acc += F[a][i] * ln[a];
-                        lam[i] = acc;
-                    }
-                    lam[IEY] += T(2) * z[IEY]; lam[IEPSI] += T(2) * z[IEPSI];
+                    for (int a = 0; a < NA; a++) if (fmask(a, NA + j)) gu += F[a][NA + j] * ln[a];
+                    stat = fmax(stat, fabs(gu));
                 }
 #pragma unroll
-                for (int i = 0; i < NZ; i++) w.Lam(k, i) = lam[i];
+                for (int i = 0; i < NA; i++) {
+                    T acc = gw[i];
+#pragma unroll
+                    for (int a = 0; a < NA; a++) if (fmask(a, i)) acc += F[a][i] * ln[a];
+                    lam[i] = acc;
+                }
             }
-            need_back = 1;
+            lam[IEY] += T(2) * ey; lam[IEPSI] += T(2) * epsi;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) w.Lam(k, i) = lam[i];
         }
-        // ---- convergence test and barrier update (only with fresh residuals: ls == 0, reg change alone
-        //      does not alter them, so repeating the test is harmless)
+    }
+
+    // convergence test, exits, barrier update.  Residuals are those of the last adjoint sweep; a
+    // regularisation change alone does not alter them, so repeating the test is harmless.
+    IGT_HD void test_and_update()
+    {
         if (stat <= P.tol * fmax(T(1), s_max) && rp <= P.tol_rp && sy_max <= P.tol_comp) {
             status = 0; done = true;
             return;
@@ -815,236 +1002,225 @@ struct Solver {
                fmax(fmax(stat, rp), fmax(fabs(sy_max - mu), fabs(sy_min - mu))) <= P.kappa_eps * mu)
             mu = fmax(P.mu_floor, fmin(P.kappa_mu * mu, pow(mu, P.theta_mu)));
         phi = Jcur - tcur.V - mu * lgcur;
-        // ---- sweep 3: Riccati
-        for (;;) {
-            bool ok = true;
-            T Vx[NA], Vxx[45];
-            {
-#pragma unroll
-                for (int i = 0; i < 45; i++) Vxx[i] = T(0);
-#pragma unroll
-                for (int i = 0; i < NA; i++) Vx[i] = T(0);
-                T z[NZ], up[2], u[2] = { T(0), T(0) };
-                load_z(b, N, z); load_up(b, N, up);
-                Vx[IEY] = T(2) * z[IEY]; Vx[IEPSI] = T(2) * z[IEPSI];
-                Vx[IS] -= tcur.gs; Vx[IV] -= tcur.gv;
-                Vxx[sym9(IEY, IEY)] = T(2); Vxx[sym9(IEPSI, IEPSI)] = T(2);
-                Vxx[sym9(IS, IS)] -= tcur.Hss; Vxx[sym9(IS, IV)] -= tcur.Hsv; Vxx[sym9(IV, IV)] -= tcur.Hvv;
-                int o = row_off(N, P.n_cinf, N);
-                visit_rows(P, N, z, up, u, ox(N), oy(N), [&](int r, T c, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
-                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-                    T s = w.S(b, o + r), y = w.Y(b, o + r);
-                    T iy = T(1) / y, rhat = s * c + mu, sig = s * iy, gr = s + rhat * iy;
-                    Vx[i0] += g0 * gr;
-                    Vxx[sym9(i0, i0)] += sig * g0 * g0;
-                    if constexpr (i1 >= 0) {
-                        Vx[i1] += g1 * gr;
-                        Vxx[sym9(i1, i1)] += sig * g1 * g1;
-                        Vxx[sym9(i0, i1)] += sig * g0 * g1;
-                    }
-                    if constexpr (i0 == IX) {
-                        Vxx[sym9(IX, IX)] += s * hxx; Vxx[sym9(IX, IY)] += s * hxy; Vxx[sym9(IY, IY)] += s * hyy;
-                    }
-                });
-            }
-            for (int k = N - 1; k >= 0; k--) {
-                T z[NZ], up[2], u[2] = { w.U(b, k, 0), w.U(b, k, 1) };
-                prefetch_stage(b, k - 1, true, true, false);
-                load_z(b, k, z); load_up(b, k, up);
-                T S[NZ][NSEED], F[NA][NW];
-#pragma unroll
-                for (int i = 0; i < NZ; i++)
-#pragma unroll
-                    for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
-                build_F(P, S, F);
-                T g[NW], H[66];
-                // g = F' Vx,  H = F' Vxx F   (structural zeros skipped at compile time)
-                T VF[NA][NW];
-#pragma unroll
-                for (int a = 0; a < NA; a++)
-#pragma unroll
-                    for (int j = 0; j < NW; j++) {
-                        T acc = T(0);
-#pragma unroll
-                        for (int c = 0; c < NA; c++) if (fmask(c, j)) acc += Vxx[sym9(a, c)] * F[c][j];
-                        VF[a][j] = acc;
-                    }
-#pragma unroll
-                for (int i = 0; i < NW; i++) {
-                    T acc = T(0);
-#pragma unroll
-                    for (int a = 0; a < NA; a++) if (fmask(a, i)) acc += F[a][i] * Vx[a];
-                    g[i] = acc;
-#pragma unroll
-                    for (int j = i; j < NW; j++) {
-                        T hh = T(0);
-#pragma unroll
-                        for (int a = 0; a < NA; a++) if (fmask(a, i)) hh += F[a][i] * VF[a][j];
-                        H[sym11(i, j)] = hh;
-                    }
-                }
-                // stage cost (mpc.py:359-364)
-                g[IEY] += T(2) * z[IEY]; g[IEPSI] += T(2) * z[IEPSI];
-                g[IUA] += T(2) * P.w_u * u[0]; g[IUD] += T(2) * P.w_u * u[1];
-                H[sym11(IEY, IEY)] += T(2); H[sym11(IEPSI, IEPSI)] += T(2);
-                H[sym11(IUA, IUA)] += T(2) * P.w_u; H[sym11(IUD, IUD)] += T(2) * P.w_u;
-                if (P.second_order) {
-                    T ln[NZ];
-#pragma unroll
-                    for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
-                    add_dyn_hessian(P, z, u[1], curv, ln, H);
-                }
-                int o = row_off(N, P.n_cinf, k);
-                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
-                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-                    T s = w.S(b, o + r), y = w.Y(b, o + r);
-                    T iy = T(1) / y, rhat = s * c + mu, sig = s * iy, gr = s + rhat * iy;
-                    g[i0] += g0 * gr;
-                    H[sym11(i0, i0)] += sig * g0 * g0;
-                    if constexpr (i1 >= 0) {
-                        g[i1] += g1 * gr;
-                        H[sym11(i1, i1)] += sig * g1 * g1;
-                        H[sym11(i0, i1)] += sig * g0 * g1;
-                    }
-                    if constexpr (i0 == IX) {
-                        H[sym11(IX, IX)] += s * hxx; H[sym11(IX, IY)] += s * hxy; H[sym11(IY, IY)] += s * hyy;
-                    }
-                });
-                T q00 = H[sym11(IUA, IUA)] + reg, q11 = H[sym11(IUD, IUD)] + reg, q01 = H[sym11(IUA, IUD)];
-                T det = q00 * q11 - q01 * q01;
-                if (!(q00 > T(0) && det > T(1e-12) * q00 * q11)) { ok = false; break; }
-                T idet = T(1) / det;
-                T i00 = q11 * idet, i11 = q00 * idet, i01 = -q01 * idet;
-                T k0 = -(i00 * g[IUA] + i01 * g[IUD]), k1 = -(i01 * g[IUA] + i11 * g[IUD]);
-                T K0[NA], K1[NA];
-#pragma unroll
-                for (int j = 0; j < NA; j++) {
-                    T ha = H[sym11(j, IUA)], hd = H[sym11(j, IUD)];
-                    K0[j] = -(i00 * ha + i01 * hd);
-                    K1[j] = -(i01 * ha + i11 * hd);
-                    w.KK(k, 0, j) = K0[j]; w.KK(k, 1, j) = K1[j];
-                }
-                w.ku(k, 0) = k0; w.ku(k, 1) = k1;
-                T haa = H[sym11(IUA, IUA)], had = H[sym11(IUA, IUD)], hdd = H[sym11(IUD, IUD)];
-                T qk0 = haa * k0 + had * k1, qk1 = had * k0 + hdd * k1;
-#pragma unroll
-                for (int i = 0; i < NA; i++)
-                    Vx[i] = g[i] + K0[i] * (g[IUA] + qk0) + K1[i] * (g[IUD] + qk1) + H[sym11(i, IUA)] * k0 + H[sym11(i, IUD)] * k1;
-#pragma unroll
-                for (int i = 0; i < NA; i++)
-#pragma unroll
-                    for (int j = i; j < NA; j++) {
-                        T QK0j = haa * K0[j] + had * K1[j], QK1j = had * K0[j] + hdd * K1[j];
-                        Vxx[sym9(i, j)] = H[sym11(i, j)] + K0[i] * QK0j + K1[i] * QK1j
-                                          + K0[i] * H[sym11(j, IUA)] + K1[i] * H[sym11(j, IUD)]
-                                          + H[sym11(i, IUA)] * K0[j] + H[sym11(i, IUD)] * K1[j];
-                    }
-            }
-            if (ok) break;
-            reg = fmax(reg * P.reg_up, P.reg_min);
-            if (reg > P.reg_max) { status = 3; done = true; return; }
-        }
-        need_back = 0;
-        ls = 0;
-        // ---- largest step keeping every slack inside the fraction-to-boundary rule on the
-        //      LINEARISED closed-loop model (d zeta+ = F [d zeta; d u], d u = ku + Ku d zeta)
-        {
-            const T tau = fmax(P.tau_min, T(1) - mu);
-            T a = T(1), dz[NA];
-#pragma unroll
-            for (int i = 0; i < NA; i++) dz[i] = T(0);
-            for (int k = 0; k <= N; k++) {
-                T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
-                prefetch_stage(b, k + 1, true, true, true);
-                load_z(b, k, z); load_up(b, k, up);
-#pragma unroll
-                for (int i = 0; i < NA; i++) dw[i] = dz[i];
-                dw[IUA] = T(0); dw[IUD] = T(0);
-                if (k < N) {
-                    u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1);
-                    T d0 = w.ku(k, 0), d1 = w.ku(k, 1);
-#pragma unroll
-                    for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dz[j]; d1 += w.KK(k, 1, j) * dz[j]; }
-                    dw[IUA] = d0; dw[IUD] = d1;
-                }
-                int o = row_off(N, P.n_cinf, k);
-                visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
-                    constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-                    T y = w.Y(b, o + r);
-                    T dc = g0 * dw[i0];
-                    if constexpr (i1 >= 0) dc += g1 * dw[i1];
-                    T dy = -(c + y) - dc;
-                    if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
-                });
-                if (k == N) break;
-                T S[NZ][NSEED], F[NA][NW];
-#pragma unroll
-                for (int i = 0; i < NZ; i++)
-#pragma unroll
-                    for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
-                build_F(P, S, F);
-#pragma unroll
-                for (int i = 0; i < NA; i++) {
-                    T acc = T(0);
-#pragma unroll
-                    for (int j = 0; j < NW; j++) if (fmask(i, j)) acc += F[i][j] * dw[j];
-                    dz[i] = acc;
-                }
-            }
-            alpha = a * P.alpha_safety;
-        }
     }
 
-    // one closed-loop forward pass with step alpha from buffer cur into buffer 1-cur
-    IGT_HD void forward_trial()
+    // sweep 3: Riccati recursion on the perturbed KKT system; node-local terms come from
+    // node_phase2.  Returns false if some Quu + reg I is not positive definite.
+    IGT_HD bool riccati_sweep()
     {
-        const int N = P.N, b = cur, nb = 1 - cur;
-        const T tau = fmax(P.tau_min, T(1) - mu);
-        T zn[NZ], upn[2] = { uprev[0], uprev[1] };
-        T J = T(0), su = T(0), th = T(0);
-        LogSum<T> lg;
-        bool fail = false;
+        const int N = P.N, b = cur;
+        T Vx[NA], Vxx[45];
+        {
+            T g[NW], H[66];
 #pragma unroll
-        for (int i = 0; i < NZ; i++) { zn[i] = x0[i]; w.Z(nb, 0, i) = zn[i]; }
+            for (int i = 0; i < NW; i++) g[i] = T(0);
+#pragma unroll
+            for (int i = 0; i < 66; i++) H[i] = T(0);
+#pragma unroll
+            for (int e = 0; e < NGE; e++) g[ge_idx(e)] = w.Gl(N, e);
+#pragma unroll
+            for (int e = 0; e < 5; e++) H[sym11(he_i(e), he_j(e))] = w.Hl(N, e);     // terminal rows: ey, collision
+#pragma unroll
+            for (int i = 0; i < NA; i++) {
+                Vx[i] = g[i];
+#pragma unroll
+                for (int j = i; j < NA; j++) Vxx[sym9(i, j)] = H[sym11(i, j)];
+            }
+            Vx[IEY] += T(2) * w.Z(b, N, IEY); Vx[IEPSI] += T(2) * w.Z(b, N, IEPSI);
+            Vx[IS] -= tcur.gs; Vx[IV] -= tcur.gv;
+            Vxx[sym9(IEY, IEY)] += T(2); Vxx[sym9(IEPSI, IEPSI)] += T(2);
+            Vxx[sym9(IS, IS)] -= tcur.Hss; Vxx[sym9(IS, IV)] -= tcur.Hsv; Vxx[sym9(IV, IV)] -= tcur.Hvv;
+        }
+        for (int k = N - 1; k >= 0; k--) {
+            T S[NZ][NSEED], F[NA][NW];
+            prefetch_back(b, k - 1, true);
+#pragma unroll
+            for (int i = 0; i < NZ; i++)
+#pragma unroll
+                for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
+            build_F(P, S, F);
+            T g[NW], H[66];
+            // g = F' Vx,  H = F' Vxx F   (structural zeros skipped at compile time)
+            T VF[NA][NW];
+#pragma unroll
+            for (int a = 0; a < NA; a++)
+#pragma unroll
+                for (int j = 0; j < NW; j++) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int c = 0; c < NA; c++) if (fmask(c, j)) acc += Vxx[sym9(a, c)] * F[c][j];
+                    VF[a][j] = acc;
+                }
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                T acc = T(0);
+#pragma unroll
+                for (int a = 0; a < NA; a++) if (fmask(a, i)) acc += F[a][i] * Vx[a];
+                g[i] = acc;
+#pragma unroll
+                for (int j = i; j < NW; j++) {
+                    T hh = T(0);
+#pragma unroll
+                    for (int a = 0; a < NA; a++) if (fmask(a, i)) hh += F[a][i] * VF[a][j];
+                    H[sym11(i, j)] = hh;
+                }
+            }
+            // stage cost (mpc.py:359-364) and the node-local terms
+            g[IEY] += T(2) * w.Z(b, k, IEY); g[IEPSI] += T(2) * w.Z(b, k, IEPSI);
+            g[IUA] += T(2) * P.w_u * w.U(b, k, 0); g[IUD] += T(2) * P.w_u * w.U(b, k, 1);
+            H[sym11(IEY, IEY)] += T(2); H[sym11(IEPSI, IEPSI)] += T(2);
+            H[sym11(IUA, IUA)] += T(2) * P.w_u; H[sym11(IUD, IUD)] += T(2) * P.w_u;
+#pragma unroll
+            for (int e = 0; e < NGE; e++) g[ge_idx(e)] += w.Gl(k, e);
+#pragma unroll
+            for (int e = 0; e < NHE; e++) H[sym11(he_i(e), he_j(e))] += w.Hl(k, e);
+            T q00 = H[sym11(IUA, IUA)] + reg, q11 = H[sym11(IUD, IUD)] + reg, q01 = H[sym11(IUA, IUD)];
+            T det = q00 * q11 - q01 * q01;
+            if (!(q00 > T(0) && det > T(1e-12) * q00 * q11)) return false;
+            T idet = T(1) / det;
+            T i00 = q11 * idet, i11 = q00 * idet, i01 = -q01 * idet;
+            T k0 = -(i00 * g[IUA] + i01 * g[IUD]), k1 = -(i01 * g[IUA] + i11 * g[IUD]);
+            T K0[NA], K1[NA];
+#pragma unroll
+            for (int j = 0; j < NA; j++) {
+                T ha = H[sym11(j, IUA)], hd = H[sym11(j, IUD)];
+                K0[j] = -(i00 * ha + i01 * hd);
+                K1[j] = -(i01 * ha + i11 * hd);
+                w.KK(k, 0, j) = K0[j]; w.KK(k, 1, j) = K1[j];
+            }
+            w.ku(k, 0) = k0; w.ku(k, 1) = k1;
+            // (Quu + reg I) [k K] = -[g_u H_ux], so the value function of the stage reduces to the Schur
+            // complement form; the reg terms keep it exact when Quu had to be regularised
+            const T rk0 = reg * k0, rk1 = reg * k1;
+#pragma unroll
+            for (int i = 0; i < NA; i++)
+                Vx[i] = g[i] + H[sym11(i, IUA)] * k0 + H[sym11(i, IUD)] * k1 - K0[i] * rk0 - K1[i] * rk1;
+#pragma unroll
+            for (int i = 0; i < NA; i++)
+#pragma unroll
+                for (int j = i; j < NA; j++)
+                    Vxx[sym9(i, j)] = H[sym11(i, j)] + H[sym11(i, IUA)] * K0[j] + H[sym11(i, IUD)] * K1[j]
+                                      - reg * (K0[i] * K0[j] + K1[i] * K1[j]);
+        }
+        return true;
+    }
+
+    // largest step keeping every slack inside the fraction-to-boundary rule on the LINEARISED
+    // closed-loop model (d zeta+ = F [d zeta; d u], d u = ku + Ku d zeta)
+    IGT_HD void step_bound()
+    {
+        const int N = P.N, b = cur;
+        const T tau = fmax(P.tau_min, T(1) - mu);
+        T a = T(1), dz[NA];
+#pragma unroll
+        for (int i = 0; i < NA; i++) dz[i] = T(0);
         for (int k = 0; k <= N; k++) {
             T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
-            prefetch_stage(b, k + 1, true, false, true);
+            prefetch_stage(b, k + 1, true, true, true);
             load_z(b, k, z); load_up(b, k, up);
 #pragma unroll
-            for (int i = 0; i < NZ; i++) dw[i] = zn[i] - z[i];
-            dw[IPA] = upn[0] - up[0]; dw[IPD] = upn[1] - up[1];
+            for (int i = 0; i < NA; i++) dw[i] = dz[i];
             dw[IUA] = T(0); dw[IUD] = T(0);
             if (k < N) {
                 u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1);
-                T d0 = alpha * w.ku(k, 0), d1 = alpha * w.ku(k, 1);
+                T d0 = w.ku(k, 0), d1 = w.ku(k, 1);
 #pragma unroll
-                for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dw[j]; d1 += w.KK(k, 1, j) * dw[j]; }
+                for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dz[j]; d1 += w.KK(k, 1, j) * dz[j]; }
                 dw[IUA] = d0; dw[IUD] = d1;
             }
             int o = row_off(N, P.n_cinf, k);
             visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
                 constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-                T s = w.S(b, o + r), y = w.Y(b, o + r);
+                T y = w.Y(b, o + r);
                 T dc = g0 * dw[i0];
                 if constexpr (i1 >= 0) dc += g1 * dw[i1];
-                T yn = y - alpha * (c + y) - dc;
-                T sn = s + (alpha * (s * c + mu) + s * dc) / y;
-                if (yn < (T(1) - tau) * y) fail = true;                 // fraction to the boundary
-                sn = fmax(sn, (T(1) - tau) * s);                        // multiplier safeguard
-                w.Y(nb, o + r) = yn; w.S(nb, o + r) = sn;
+                T dy = -(c + y) - dc;
+                if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
             });
-            if (fail) break;
-            T un[2] = { u[0] + dw[IUA], u[1] + dw[IUD] };
-            // rows at the new point: infeasibility and barrier terms
-            visit_rows(P, k, zn, upn, un, ox(k), oy(k), [&](int r, T c, auto, T, auto, T, T, T, T) {
-                T yn = w.Y(nb, o + r);
-                th += fabs(c + yn);
-                lg.add(yn);
-            });
-            J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
             if (k == N) break;
+            T S[NZ][NSEED], F[NA][NW];
+#pragma unroll
+            for (int i = 0; i < NZ; i++)
+#pragma unroll
+                for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
+            build_F(P, S, F);
+#pragma unroll
+            for (int i = 0; i < NA; i++) {
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < NW; j++) if (fmask(i, j)) acc += F[i][j] * dw[j];
+                dz[i] = acc;
+            }
+        }
+        alpha = a * P.alpha_safety;
+    }
+
+    // The backward pass is split so that the kernels can run the node-local work of all stages of
+    // all problems of a CTA in parallel (node_phase1 / node_phase2) between the sequential sweeps:
+    //   [node_phase1 of every node]  backward_pre()  [node_phase2 of every node]  backward_post()
+    // backward_pre: adjoint sweep (if the iterate changed), convergence test, barrier update.
+    // Returns true if node_phase2 has to run before backward_post (fresh iterate, still going).
+    IGT_HD bool backward_pre()
+    {
+        const bool fresh = need_back == 2;
+        if (fresh) { adjoint_sweep(); need_back = 1; }
+        test_and_update();
+        return fresh && !done;
+    }
+
+    // backward_post: Riccati sweep (regularisation raised until it succeeds) and the step bound
+    IGT_HD void backward_post()
+    {
+        for (;;) {
+            if (riccati_sweep()) break;
+            reg = fmax(reg * P.reg_up, P.reg_min);
+            if (reg > P.reg_max) { status = 3; done = true; return; }
+        }
+        need_back = 0;
+        ls = 0;
+        step_bound();
+    }
+
+    // whole backward pass by one thread (tests/hostsim; the kernels interleave the CTA-wide phases)
+    IGT_HD void backward()
+    {
+        if (need_back == 2) {
+            const NodeCtx<T> c = node_ctx();
+            for (int k = 0; k <= P.N; k++) node_phase1(P, w, c, k);
+        }
+        if (backward_pre()) {
+            const NodeCtx<T> c = node_ctx();
+            for (int k = 0; k <= P.N; k++) node_phase2(P, w, c, k);
+        }
+        if (!done) backward_post();
+    }
+
+    // closed-loop nonlinear rollout with step alpha from buffer cur into buffer 1-cur (controls and
+    // states only; the rows of the trial point are evaluated by node_phase3).  Sets trial_ok = false
+    // if the rollout left the finite range.
+    IGT_HD void forward_rollout()
+    {
+        const int N = P.N, b = cur, nb = 1 - cur;
+        T zn[NZ], upn[2] = { uprev[0], uprev[1] };
+        T J = T(0), su = T(0);
+        bool fail = false;
+#pragma unroll
+        for (int i = 0; i < NZ; i++) { zn[i] = x0[i]; w.Z(nb, 0, i) = zn[i]; }
+        for (int k = 0; k < N; k++) {
+            T dw[NA];
+            prefetch_stage(b, k + 1, false, false, true);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) dw[i] = zn[i] - w.Z(b, k, i);
+            if (k == 0) { dw[IPA] = T(0); dw[IPD] = T(0); }
+            else { dw[IPA] = upn[0] - w.U(b, k - 1, 0); dw[IPD] = upn[1] - w.U(b, k - 1, 1); }
+            T d0 = alpha * w.ku(k, 0), d1 = alpha * w.ku(k, 1);
+#pragma unroll
+            for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dw[j]; d1 += w.KK(k, 1, j) * dw[j]; }
+            T un[2] = { w.U(b, k, 0) + d0, w.U(b, k, 1) + d1 };
+            J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
             su += un[0] * un[0] + un[1] * un[1];
             w.U(nb, k, 0) = un[0]; w.U(nb, k, 1) = un[1];
+            w.Du(k, 0) = d0; w.Du(k, 1) = d1;
             T zz[NZ];
             rk4_step(P, zn, un, curv, zz);
             bool fin = true;
@@ -1053,8 +1229,28 @@ struct Solver {
             if (!fin) { fail = true; break; }
             upn[0] = un[0]; upn[1] = un[1];
         }
+        J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
         trial_ok = !fail;
-        Jcand = J + P.w_u * su; lgcand = lg.total(); thetacand = th;
+        Jcand = J + P.w_u * su;
+    }
+
+    // gather the per-node results of node_phase3 of the trial point
+    IGT_HD void collect_trial()
+    {
+        T th = T(0), lg = T(0), bad = T(0);
+        for (int k = 0; k <= P.N; k++) { th += w.Tr(k, 0); lg += w.Tr(k, 1); bad += w.Tr(k, 2); }
+        thetacand = th; lgcand = lg;
+        if (bad > T(0)) trial_ok = false;
+    }
+
+    // one trial step by one thread (tests/hostsim; the kernels run node_phase3 CTA-wide)
+    IGT_HD void forward_trial()
+    {
+        forward_rollout();
+        if (!trial_ok) return;
+        const NodeCtx<T> c = node_ctx();
+        for (int k = 0; k <= P.N; k++) node_phase3(P, w, c, k);
+        collect_trial();
     }
 
     // acceptance test (needs tcand of the candidate's terminal state when trial_ok)
@@ -1208,20 +1404,27 @@ __device__ __forceinline__ void term_from_tc(const float *o, TermVal<T> &t)
 
 // TC = true: the gt_mpc value term of all 256 problems of the CTA is evaluated together on the
 // tensor cores (mlp_tc.cuh) at the two CTA-uniform points of the loop where it is needed.
-// CTA-wide sweep 1.  The sensitivities of a stage depend only on that stage's (z_k, u_k), so the
-// (problem, stage) pairs of every problem of the CTA that needs a full backward pass are independent
-// work items; they are dealt out over all threads of the CTA.  Every lane is busy whatever the
-// mix of per-problem states, a lone straggler gets its N stages done by N threads at once, and the
-// loop body (one RK4 step with tangents) is small enough to stay in the instruction cache.
+// CTA-wide node phases.  The node-local work of an iteration (node_phase1: sensitivities and row
+// summaries; node_phase2: perturbed-KKT terms of the rows and the dynamics second-order term)
+// depends only on that node's (z_k, u_k, y, s) and on a few per-problem scalars, so the (problem,
+// node) pairs of every problem of the CTA that needs the phase are independent work items; they
+// are dealt out over all threads of the CTA.  Every lane is busy whatever the mix of per-problem
+// states, a lone straggler gets its N + 1 nodes done by N + 1 threads at once, and the loop body is
+// small enough to stay in the instruction cache.
 constexpr int MAX_SOLVE_BLOCK = 256;
 template <typename T>
-__device__ __forceinline__ void sens_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
-                                               long bound, int cur, const T *curv)
+struct NodeList {                    // shared-memory work list of one CTA-wide phase
+    int wcnt[MAX_SOLVE_BLOCK / 32];
+    int slot[MAX_SOLVE_BLOCK];
+    NodeCtx<T> ctx[MAX_SOLVE_BLOCK];
+};
+
+template <typename T, int PHASE>
+__device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
+                                               long bound, const Solver<T> &sv, NodeList<T> &nl)
 {
-    __shared__ int s_wcnt[MAX_SOLVE_BLOCK / 32];
-    __shared__ int s_slot[MAX_SOLVE_BLOCK];
-    __shared__ int s_cur[MAX_SOLVE_BLOCK];
-    __shared__ T s_curv[3][MAX_SOLVE_BLOCK];
+    int *s_wcnt = nl.wcnt, *s_slot = nl.slot;
+    NodeCtx<T> *s_ctx = nl.ctx;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const unsigned m = __ballot_sync(FULL, need);
@@ -1231,18 +1434,19 @@ __device__ __forceinline__ void sens_phase_cta(const DevParams<T> &P, T *ws_base
     for (int i = 0; i < nw; i++) { int c = s_wcnt[i]; if (i < warp) base += c; n += c; }
     if (need) {
         const int idx = base + __popc(m & ((1u << lane) - 1u));
-        s_slot[idx] = (int)bound; s_cur[idx] = cur;
-        s_curv[0][idx] = curv[0]; s_curv[1][idx] = curv[1]; s_curv[2][idx] = curv[2];
+        s_slot[idx] = (int)bound;
+        s_ctx[idx] = sv.node_ctx();
     }
     __syncthreads();
     if (n > 0) {
         Ws<T> w; w.L = L;
-        const int total = n * P.N;
+        const int total = n * (P.N + 1);
         for (int it = tid; it < total; it += blockDim.x) {
             const int j = it % n, k = it / n;
             w.bind(ws_base, s_slot[j]);
-            const T cv[3] = { s_curv[0][j], s_curv[1][j], s_curv[2][j] };
-            sens_stage(P, w, s_cur[j], k, cv);
+            if (PHASE == 1) node_phase1(P, w, s_ctx[j], k);
+            else if (PHASE == 2) node_phase2(P, w, s_ctx[j], k);
+            else node_phase3(P, w, s_ctx[j], k);
         }
     }
     __syncthreads();
@@ -1254,11 +1458,11 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
                                                  const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc,
                                                  int quota)
 {
+    __shared__ NodeList<T> nl;
     Solver<T> sv(P);
     sv.w.L.init(P.N, P.n_cinf);
     sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
-    sv.sens_external = true;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     // only the first `quota` threads of a CTA fetch fresh problems, so that a batch smaller than the
@@ -1341,15 +1545,21 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
                 if (n > 0) since_adopt = 0;
             }
         }
+        const int cta_busy = __syncthreads_or(active);
         if (__syncthreads_and(wants_exit)) break;
-        // ---- phase 1a: sensitivities, CTA-wide ----
-        sens_phase_cta(P, ws_base, sv.w.L, active && sv.need_back == 2, bound, sv.cur, sv.curv);
-        // ---- phase 1b: adjoint, Riccati, step bound (per problem) ----
-        if (active && sv.need_back) sv.backward();
+        if (!cta_busy) { __nanosleep(2000); since_adopt++; continue; }   // nothing to do here: poll the queue gently
+        // ---- phase 1: backward pass = CTA-wide node phases between the per-problem sweeps ----
+        const bool back = active && sv.need_back;
+        node_phase_cta<T, 1>(P, ws_base, sv.w.L, back && sv.need_back == 2, bound, sv, nl);
+        const bool p2 = back && sv.backward_pre();              // adjoint sweep, convergence test, barrier update
+        node_phase_cta<T, 2>(P, ws_base, sv.w.L, p2, bound, sv, nl);
+        if (back && !sv.done) sv.backward_post();               // Riccati sweep, step bound
         __syncthreads();
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
-        if (trying) sv.forward_trial();
+        if (trying) sv.forward_rollout();
+        node_phase_cta<T, 3>(P, ws_base, sv.w.L, trying && sv.trial_ok, bound, sv, nl);
+        if (trying && sv.trial_ok) sv.collect_trial();
         if (TC) {
             const bool need = trying && sv.trial_ok;
             if (__syncthreads_or(need)) {
