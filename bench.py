@@ -102,14 +102,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons}
 
 
-def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0):
+def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0, max_trials=150):
     """The oracle's C restatement timed on the host cores on the first n_sample problems."""
     from oracle import nlp, c_oracle
     P = nlp.Params(N=N)
     term = None
     if mode == "gt_mpc":
         term = nlp.MLPTerm(weights=mlp["weights"], Wn=mlp["Wn"], mu_f=mlp["mu_f"], sigma_t=mlp["sigma_t"], mu_t=mlp["mu_t"])
-    co = c_oracle.COracle(P, term, max_iter=max_iter)
+    co = c_oracle.COracle(P, term, max_iter=max_iter, max_trials=max_trials)
     co.solve(x0[:64], up[:64], cv[:64], ob[:64], n_threads=threads)           # warm the library / page in
     t0 = time.perf_counter()
     r = co.solve(x0[:n_sample], up[:n_sample], cv[:n_sample], ob[:n_sample], n_threads=threads)
@@ -286,7 +286,8 @@ def main():
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_sample = min(B, max(512, 128 * cores))
-            c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, solver.params.max_iter)
+            c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, solver.params.max_iter,
+                                 max_trials=solver.params.max_trials)
             line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "first %d problems of the same batch, oracle fp64 C restatement on all "
                                               "host threads (the reference's CasADi/IPOPT solver is not installable "

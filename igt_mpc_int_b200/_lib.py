@@ -40,7 +40,7 @@ class IgtParams(C.Structure):
         ("reg_min", C.c_double), ("reg_up", C.c_double), ("reg_down", C.c_double), ("reg_max", C.c_double),
         ("eps_phi", C.c_double), ("gamma_theta", C.c_double), ("theta_small", C.c_double),
         ("max_iter", C.c_int), ("n_alpha", C.c_int), ("second_order", C.c_int),
-        ("stall_iter", C.c_int), ("stall_rp", C.c_double), ("precision", C.c_int),
+        ("stall_iter", C.c_int), ("stall_rp", C.c_double), ("max_trials", C.c_int), ("precision", C.c_int),
     ]
 
     def set_cinf(self, A, b):

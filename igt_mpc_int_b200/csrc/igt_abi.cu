@@ -665,6 +665,17 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
 }
 
 
+#ifdef IGT_PHASE_CLOCKS
+/* debug builds only: cycle counters of thread 0 of CTA 0 of the last solve launch */
+int igt_debug_phase_clocks(igt_handle *h, long long *out16)
+{
+    if (!h || !out16) return IGT_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out16, g_phase_clk, 16 * sizeof(long long)));
+    return IGT_OK;
+}
+#endif
+
 int igt_set_option(igt_handle *h, const char *name, double value)
 {
     if (!h || !name) return IGT_EINVAL;

@@ -13,6 +13,7 @@ inline void fill_dev_params(const igt_params &p, DevParams<T> &d)
     memset(&d, 0, sizeof(d));
     d.N = p.N; d.n_rk = p.n_rk; d.n_cinf = p.n_cinf; d.max_iter = p.max_iter; d.n_alpha = p.n_alpha;
     d.second_order = p.second_order; d.n_layers = 0; d.stall_iter = p.stall_iter; d.stall_rp = T(p.stall_rp);
+    d.max_trials = p.max_trials > 0 ? p.max_trials : (1 << 30);
     d.dt = T(p.dt); d.h = T(p.dt / p.n_rk); d.l_r = T(p.l_r); d.lsum = T(p.l_r + p.l_f);
     d.inv_lr = T(1.0 / p.l_r); d.rho = T(p.l_r / (p.l_f + p.l_r));
     d.v_min = T(p.v_min); d.v_max = T(p.v_max); d.a_min = T(p.a_min); d.a_max = T(p.a_max);
@@ -42,7 +43,7 @@ inline int default_params(igt_params *p, int precision)
     p->tau_min = 0.99; p->reg_min = 1e-4; p->reg_up = 10.0; p->reg_down = 10.0; p->reg_max = 1e10;
     p->gamma_theta = 1e-6; p->max_iter = 60; p->n_alpha = 6; p->second_order = 1;
     p->mu0_warm = 1e-4; p->y_init_min_warm = 1e-3;
-    p->stall_iter = 16; p->stall_rp = 1e-2;
+    p->stall_iter = 16; p->stall_rp = 1e-2; p->max_trials = 150;
     p->precision = precision;
     if (precision == IGT_PREC_F64) {
         p->tol = 1e-6; p->tol_rp = 1e-8; p->tol_comp = 1e-7; p->mu_floor = 1e-8;

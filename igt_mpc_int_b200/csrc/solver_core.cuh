@@ -45,7 +45,7 @@ constexpr int N_GUESS = 5;
 
 template <typename T>
 struct DevParams {
-    int N, n_rk, n_cinf, max_iter, n_alpha, second_order, n_layers, stall_iter;
+    int N, n_rk, n_cinf, max_iter, n_alpha, second_order, n_layers, stall_iter, max_trials;
     int dims[MAX_MLP_LAYERS + 1];
     T dt, h, l_r, lsum, inv_lr, rho;
     T v_min, v_max, a_min, a_max, df_max, ey_lim, da_max, ddf_max, d_min, w_u;
@@ -728,7 +728,7 @@ struct Solver {
     int mlp_width;
     // iteration state
     int cur;                  // buffer holding the current iterate
-    int status, iters, ls, need_back;   // need_back: 2 = full backward, 1 = Riccati only, 0 = none
+    int status, iters, ls, need_back, trials;   // need_back: 2 = full backward, 1 = Riccati only, 0 = none
     bool done;
     T mu, reg, alpha, Jcur, lgcur, thetacur, phi;
     T stat, rp, s_max, sy_min, sy_max;
@@ -881,7 +881,7 @@ struct Solver {
     {
         const int N = P.N;
         load_inputs(io, p, has_ctx);
-        cur = 0; status = 1; iters = 0; ls = 0; need_back = 2; done = false;
+        cur = 0; status = 1; iters = 0; ls = 0; need_back = 2; done = false; trials = 0;
         mu = warm ? P.mu0_warm : P.mu0; reg = T(0); alpha = T(1);
         const T y_min = warm ? P.y_init_min_warm : P.y_init_min;
         {   // rows on x0 alone: mpc.py:316-317 and :298-299 at k = 0
@@ -1257,6 +1257,7 @@ struct Solver {
     IGT_HD void finish_trial()
     {
         bool accepted = false;
+        trials++;
         if (trial_ok) {
             T phin = Jcand - tcand.V - mu * lgcand;
             accepted = (phin == phin) && fabs(phin) < T(1e30) &&
@@ -1279,6 +1280,8 @@ struct Solver {
                 need_back = 1;
             }
         }
+        // budget of forward passes, checked between iterations like the iteration cap
+        if (!done && (accepted || need_back == 1) && trials >= P.max_trials) { status = 1; done = true; }
     }
 
     // write the outputs of this problem (x, u, cost, max row violation in reference units)
@@ -1366,7 +1369,7 @@ __device__ __forceinline__ void save_state(const Solver<T> &sv, const Sched &sc,
 {
     double *t = sc.save_t + slot * SAVE_T;
     long long *q = sc.save_i + slot * SAVE_I;
-    q[0] = p; q[1] = sv.cur; q[2] = sv.status; q[3] = sv.iters; q[4] = sv.ls; q[5] = sv.need_back;
+    q[0] = p; q[1] = sv.cur; q[2] = sv.status; q[3] = sv.iters; q[4] = sv.ls; q[5] = sv.need_back; q[6] = sv.trials;
     t[0] = sv.mu; t[1] = sv.reg; t[2] = sv.alpha; t[3] = sv.Jcur; t[4] = sv.lgcur; t[5] = sv.thetacur; t[6] = sv.phi;
     t[7] = sv.stat; t[8] = sv.rp; t[9] = sv.s_max; t[10] = sv.sy_min; t[11] = sv.sy_max;
     t[12] = sv.tcur.V; t[13] = sv.tcur.gs; t[14] = sv.tcur.gv; t[15] = sv.tcur.Hss; t[16] = sv.tcur.Hsv; t[17] = sv.tcur.Hvv;
@@ -1378,7 +1381,7 @@ __device__ __forceinline__ long restore_state(Solver<T> &sv, const Sched &sc, lo
     const double *t = sc.save_t + slot * SAVE_T;
     const long long *q = sc.save_i + slot * SAVE_I;
     long p = q[0];
-    sv.cur = (int)q[1]; sv.status = (int)q[2]; sv.iters = (int)q[3]; sv.ls = (int)q[4]; sv.need_back = (int)q[5];
+    sv.cur = (int)q[1]; sv.status = (int)q[2]; sv.iters = (int)q[3]; sv.ls = (int)q[4]; sv.need_back = (int)q[5]; sv.trials = (int)q[6];
     sv.done = false;
     sv.mu = T(t[0]); sv.reg = T(t[1]); sv.alpha = T(t[2]); sv.Jcur = T(t[3]); sv.lgcur = T(t[4]); sv.thetacur = T(t[5]);
     sv.phi = T(t[6]); sv.stat = T(t[7]); sv.rp = T(t[8]); sv.s_max = T(t[9]); sv.sy_min = T(t[10]); sv.sy_max = T(t[11]);
@@ -1411,7 +1414,10 @@ __device__ __forceinline__ void term_from_tc(const float *o, TermVal<T> &t)
 // are dealt out over all threads of the CTA.  Every lane is busy whatever the mix of per-problem
 // states, a lone straggler gets its N + 1 nodes done by N + 1 threads at once, and the loop body is
 // small enough to stay in the instruction cache.
-constexpr int MAX_SOLVE_BLOCK = 256;
+#ifndef IGT_MAX_SOLVE_BLOCK
+#define IGT_MAX_SOLVE_BLOCK 256
+#endif
+constexpr int MAX_SOLVE_BLOCK = IGT_MAX_SOLVE_BLOCK;
 template <typename T>
 struct NodeList {                    // shared-memory work list of one CTA-wide phase
     int wcnt[MAX_SOLVE_BLOCK / 32];
@@ -1452,6 +1458,15 @@ __device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base
     __syncthreads();
 }
 
+// Optional per-phase cycle counters of the first thread of CTA 0 (build with -DIGT_PHASE_CLOCKS;
+// tools/phase_clocks.py reads them through igt_debug_phase_clocks).
+#ifdef IGT_PHASE_CLOCKS
+__device__ long long g_phase_clk[16];
+#define IGT_TICK(i) do { if (clk_on) { long long t_ = clock64(); clk[i] += t_ - clk_t; clk_t = t_; } } while (0)
+#else
+#define IGT_TICK(i) do { } while (0)
+#endif
+
 template <typename T, bool TC>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
                                                  long slot, long B, const Sched &sc,
@@ -1471,6 +1486,10 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
     long p = -1, bound = slot;
     int since_adopt = DONATE_MIN_ITERS;
     if (TC) sv.phi_noise = T(3e-7);
+#ifdef IGT_PHASE_CLOCKS
+    const bool clk_on = blockIdx.x == 0 && threadIdx.x == 0;
+    long long clk[16] = { 0 }, clk_t = clock64();
+#endif
     // All warps of the CTA (one CTA per SM) walk the phases together -- scheduling, backward
     // sweeps, forward trial -- separated by CTA barriers, so that the SM's instruction cache
     // holds one phase's loop body at a time instead of eight warps' worth of different code.
@@ -1547,19 +1566,39 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         }
         const int cta_busy = __syncthreads_or(active);
         if (__syncthreads_and(wants_exit)) break;
-        if (!cta_busy) { __nanosleep(2000); since_adopt++; continue; }   // nothing to do here: poll the queue gently
+        if (!cta_busy) { __nanosleep(2000); since_adopt++; IGT_TICK(9); continue; }   // nothing to do here: poll the queue gently
+        IGT_TICK(0);
         // ---- phase 1: backward pass = CTA-wide node phases between the per-problem sweeps ----
         const bool back = active && sv.need_back;
         node_phase_cta<T, 1>(P, ws_base, sv.w.L, back && sv.need_back == 2, bound, sv, nl);
+        IGT_TICK(1);
         const bool p2 = back && sv.backward_pre();              // adjoint sweep, convergence test, barrier update
+        IGT_TICK(2);
         node_phase_cta<T, 2>(P, ws_base, sv.w.L, p2, bound, sv, nl);
-        if (back && !sv.done) sv.backward_post();               // Riccati sweep, step bound
+        IGT_TICK(3);
+        if (back && !sv.done) {                                  // Riccati sweep, step bound
+#ifdef IGT_PHASE_CLOCKS
+            for (;;) {
+                if (sv.riccati_sweep()) break;
+                sv.reg = fmax(sv.reg * P.reg_up, P.reg_min);
+                if (sv.reg > P.reg_max) { sv.status = 3; sv.done = true; break; }
+            }
+            IGT_TICK(4);
+            if (!sv.done) { sv.need_back = 0; sv.ls = 0; sv.step_bound(); }
+            IGT_TICK(5);
+#else
+            sv.backward_post();
+#endif
+        }
         __syncthreads();
+        IGT_TICK(6);
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
         if (trying) sv.forward_rollout();
+        IGT_TICK(7);
         node_phase_cta<T, 3>(P, ws_base, sv.w.L, trying && sv.trial_ok, bound, sv, nl);
         if (trying && sv.trial_ok) sv.collect_trial();
+        IGT_TICK(8);
         if (TC) {
             const bool need = trying && sv.trial_ok;
             if (__syncthreads_or(need)) {
@@ -1574,7 +1613,11 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         if (trying) sv.finish_trial();
         if (active && sv.done) { sv.write_out(io, p); active = false; atomicSub(sc.in_flight, 1); }
         since_adopt++;
+        IGT_TICK(10);
     }
+#ifdef IGT_PHASE_CLOCKS
+    if (clk_on) for (int i = 0; i < 16; i++) g_phase_clk[i] = clk[i];
+#endif
 }
 #endif
 

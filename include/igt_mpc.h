@@ -70,6 +70,9 @@ typedef struct {
     int second_order;  /* add the dt*Hess(lambda.f) curvature term to the Riccati pass */
     int stall_iter;    /* local-infeasibility exit: iteration >= stall_iter and ... */
     double stall_rp;   /* ... primal residual still above stall_rp -> IGT_STATUS_STALLED */
+    int max_trials;    /* budget of forward passes (accepted or not) per solve -> IGT_STATUS_MAXITER; a problem that
+                          burns all n_alpha halvings iteration after iteration is given up on (the reference's
+                          counterpart is IPOPT's max_wall_time, mpc.py:139) */
     int precision;     /* IGT_PREC_F32 / IGT_PREC_F64: arithmetic of the solver kernels */
 } igt_params;
 

@@ -39,7 +39,7 @@ def test_closed_loop_outcomes_match_oracle_all_scenarios():
     specs = episode.reference_episode_specs()
     gpu = BatchSolver(N=40)
     rg = episode.run_closed_loop(gpu, specs, steps=150, N=40, record_latency=True)
-    ro = episode.run_closed_loop(OracleBackend(N=40, max_iter=gpu.params.max_iter), specs, steps=150, N=40)
+    ro = episode.run_closed_loop(OracleBackend(N=40, max_iter=gpu.params.max_iter, max_trials=gpu.params.max_trials), specs, steps=150, N=40)
     assert np.array_equal(rg.deadlock, ro.deadlock)
     assert np.array_equal(rg.collision, ro.collision)
     assert np.array_equal(rg.goal, ro.goal)

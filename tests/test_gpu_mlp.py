@@ -64,7 +64,7 @@ def test_gt_mpc_solve_matches_oracle(oracle_params, hidden):
     pb = S.mid_episode(B, N=N, seed=41)
     s = BatchSolver(N=N, mlp=_as_dict(term))
     r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, nn_ctx=pb.nn_ctx)
-    o = c_oracle.COracle(oracle_params[N], term, max_iter=s.params.max_iter).solve(pb.x0, pb.u_prev, pb.curv, pb.obs,
+    o = c_oracle.COracle(oracle_params[N], term, max_iter=s.params.max_iter, max_trials=s.params.max_trials).solve(pb.x0, pb.u_prev, pb.curv, pb.obs,
                                                                                   nn_ctx=pb.nn_ctx)
     ok = (r["status"] == 0) & (o["status"] == 0)
     assert ok.sum() > 0.7 * B

@@ -6,7 +6,7 @@ from tests.util import relerr
 
 pytestmark = pytest.mark.gpu
 
-TIGHT = dict(max_iter=300)   # product defaults already use the oracle's tolerances; only the iteration cap differs
+TIGHT = dict(max_iter=300, max_trials=0)   # product defaults already use the oracle's tolerances; only the iteration cap differs
 
 
 def _solver(N, **kw):

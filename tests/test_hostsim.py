@@ -17,6 +17,7 @@ def cinf():
 
 def _tight(p):
     p.max_iter = 300      # tolerances already equal the oracle's
+    p.max_trials = 0      # no budget of forward passes, like the oracle's default
     return p
 
 
@@ -76,3 +77,15 @@ def test_core_x0_infeasible_and_warm_start(oracle_params, cinf):
     warm = H.solve(p, pb.x0, pb.u_prev, pb.curv, pb.obs, u_init=np.nan_to_num(cold["U"]))
     assert np.all(warm["status"][ok] == 0)
     assert np.max(relerr(warm["cost"][ok], cold["cost"][ok])) < 1e-4
+
+
+def test_core_iteration_and_trial_budgets_match_oracle(oracle_params, cinf):
+    """Product defaults (max_iter 60, max_trials 150 forward passes) against the oracle run with the
+    same budgets: the same problems are given up on, with the same status."""
+    pb = S.mid_episode(256, N=40, seed=2026)
+    p = H.default_params(1); p.set_cinf(*cinf)
+    assert p.max_iter == 60 and p.max_trials == 150
+    r = H.solve(p, pb.x0, pb.u_prev, pb.curv, pb.obs)
+    o = c_oracle.COracle(oracle_params[40], max_iter=p.max_iter, max_trials=p.max_trials).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    assert np.mean(r["status"] == o["status"]) >= 0.99
+    assert (r["status"] != 0).sum() > 0

@@ -1,0 +1,26 @@
+"""Per-phase cycle counters of one persistent thread (debug build of the library with -DIGT_PHASE_CLOCKS).
+usage: phase_clocks.py LIB.so B"""
+import sys, os, ctypes as C
+import numpy as np, torch
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+from igt_mpc_int_b200 import _lib
+_lib.LIB_PATH = os.path.abspath(sys.argv[1])
+from igt_mpc_int_b200 import scenarios as S
+from igt_mpc_int_b200.planner import BatchSolver
+B = int(sys.argv[2]); N = 40
+pb = S.mid_episode(B, N=N)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+x0, up, cv, ob = t(pb.x0), t(pb.u_prev), t(pb.curv), t(pb.obs)
+s = BatchSolver(N=N)
+out = s.solve_batch_device(x0, up, cv, ob); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); out = s.solve_batch_device(x0, up, cv, ob, out=out); e1.record(); torch.cuda.synchronize()
+clk = (C.c_longlong * 16)()
+lib = _lib.load()
+lib.igt_debug_phase_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+assert lib.igt_debug_phase_clocks(s._h, clk) == 0
+names = ["sched", "node1(sens,rows)", "adjoint+test", "node2(kkt)", "riccati", "step_bound", "sync", "rollout", "node3+collect", "idle", "accept+out"]
+tot = sum(clk)
+print("B=%d ms=%.1f total cycles %.3e (%.1f ms @1.965GHz)" % (B, e0.elapsed_time(e1), tot, tot / 1.965e6))
+for n, c in zip(names, clk):
+    print("%-18s %12d  %5.1f%%" % (n, c, 100.0 * c / max(tot, 1)))
