@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons}
 
 
-def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0, max_trials=150):
+def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0, max_trials=0):
     """The oracle's C restatement timed on the host cores on the first n_sample problems."""
     from oracle import nlp, c_oracle
     P = nlp.Params(N=N)

@@ -294,6 +294,7 @@ int igt_create(const igt_params *p, igt_handle **out)
         g_create_err = "unsupported N / n_rk / n_cinf / precision";
         return IGT_EINVAL;
     }
+    if (p->n_alpha < 1 || p->n_alpha > MAX_ALPHA) { g_create_err = "n_alpha must be in 1..6"; return IGT_EINVAL; }
     igt_handle *h = new (std::nothrow) igt_handle();
     if (!h) { g_create_err = "out of memory"; return IGT_EINVAL; }
     h->prm = *p;

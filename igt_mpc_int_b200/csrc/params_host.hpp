@@ -43,7 +43,7 @@ inline int default_params(igt_params *p, int precision)
     p->tau_min = 0.99; p->reg_min = 1e-4; p->reg_up = 10.0; p->reg_down = 10.0; p->reg_max = 1e10;
     p->gamma_theta = 1e-6; p->max_iter = 60; p->n_alpha = 6; p->second_order = 1;
     p->mu0_warm = 1e-4; p->y_init_min_warm = 1e-3;
-    p->stall_iter = 16; p->stall_rp = 1e-2; p->max_trials = 150;
+    p->stall_iter = 16; p->stall_rp = 1e-2; p->max_trials = 0;
     p->precision = precision;
     if (precision == IGT_PREC_F64) {
         p->tol = 1e-6; p->tol_rp = 1e-8; p->tol_comp = 1e-7; p->mu_floor = 1e-8;

@@ -40,6 +40,13 @@ constexpr int MAX_CINF = 128;
 // w = (zeta, u) and, together with the dynamics second-order term, 22 entries of the symmetric
 // w-space Hessian; these are what the sequential sweeps need from a node.
 constexpr int NGE = 8, NHE = 22;
+// Iterate buffers per workspace slot: the current iterate plus one buffer per step halving of a line
+// search, so that all candidates alpha, alpha/2, ... of an iteration can be rolled out at once when
+// lanes are idle (speculative line search, see trial_phase_cta).  Candidate j of an iterate living in
+// buffer `cur` goes to the j-th buffer other than `cur`, so that the usual case (first candidate
+// accepted) keeps toggling between buffers 0 and 1 and the speculative buffers stay cold.
+constexpr int MAX_ALPHA = 6, NBUF = MAX_ALPHA + 1;
+IGT_HD constexpr int cand_buf(int cur, int j) { return j < cur ? j : j + 1; }
 constexpr int MAX_MLP_LAYERS = 5;
 constexpr int N_GUESS = 5;
 
@@ -71,16 +78,16 @@ IGT_HD int row_total(int N, int n_cinf) { return row_off(N, n_cinf, N) + 3; }
 
 struct WsLayout {
     int N, M;
-    int oZ[2], oU[2], oY[2], oS[2], oSens, oLam, oKu, oKK, oGw, oRed, oGl, oHl, oTr, oDu, total;
+    int oZ[NBUF], oU[NBUF], oY[NBUF], oS[NBUF], oTc, oSens, oLam, oKu, oKK, oGw, oRed, oGl, oHl, oTr, oDu, total;
     IGT_HD void init(int N_, int n_cinf)
     {
         N = N_;
         M = row_total(N, n_cinf);
         int o = 0;
-        for (int b = 0; b < 2; b++) { oZ[b] = o; o += NZ * (N + 1); }
-        for (int b = 0; b < 2; b++) { oU[b] = o; o += 2 * N; }
-        for (int b = 0; b < 2; b++) { oY[b] = o; o += M; }
-        for (int b = 0; b < 2; b++) { oS[b] = o; o += M; }
+        for (int b = 0; b < NBUF; b++) { oZ[b] = o; o += NZ * (N + 1); }
+        for (int b = 0; b < NBUF; b++) { oU[b] = o; o += 2 * N; }
+        for (int b = 0; b < NBUF; b++) { oY[b] = o; o += M; }
+        for (int b = 0; b < NBUF; b++) { oS[b] = o; o += M; }
         oSens = o; o += NZ * NSEED * N;
         oLam = o;  o += NZ * (N + 1);
         oKu = o;   o += 2 * N;
@@ -89,8 +96,9 @@ struct WsLayout {
         oRed = o;  o += 4 * (N + 1);
         oGl = o;   o += NGE * (N + 1);
         oHl = o;   o += NHE * (N + 1);
-        oTr = o;   o += 3 * (N + 1);       // per-node results of a trial step, see node_phase3
-        oDu = o;   o += 2 * N;             // control change of the trial step (exact, not new - old)
+        oTr = o;   o += NBUF * 3 * (N + 1);  // per-node results of a trial step, see node_phase3
+        oDu = o;   o += NBUF * 2 * N;        // control change of a trial step (exact, not new - old)
+        oTc = o;   o += NBUF * 2;            // per-candidate rollout results: finite flag, cost
         total = o;
     }
 };
@@ -123,8 +131,9 @@ struct Ws {
     IGT_HD T &Red(int k, int e) const { return at(L.oRed + k * 4 + e); }
     IGT_HD T &Gl(int k, int e) const { return at(L.oGl + k * NGE + e); }
     IGT_HD T &Hl(int k, int e) const { return at(L.oHl + k * NHE + e); }
-    IGT_HD T &Tr(int k, int e) const { return at(L.oTr + k * 3 + e); }
-    IGT_HD T &Du(int k, int i) const { return at(L.oDu + k * 2 + i); }
+    IGT_HD T &Tr(int b, int k, int e) const { return at(L.oTr + (b * (L.N + 1) + k) * 3 + e); }
+    IGT_HD T &Du(int b, int k, int i) const { return at(L.oDu + (b * L.N + k) * 2 + i); }
+    IGT_HD T &Tc(int b, int e) const { return at(L.oTc + b * 2 + e); }
 };
 
 // problem inputs / outputs: batch-major AoS arrays exactly as the C ABI receives them
@@ -240,9 +249,10 @@ IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const
 // (kinematic_bicycle_model_frenet.py:111) -- reproduced on purpose.  The four stages run as a
 // loop (one copy of the right-hand side in the instruction stream, not sixteen).
 template <typename T>
-IGT_HDN void rk4_step(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn)
+IGT_HDN void rk4_step(const DevParams<T> &P, const T *z0, const T *u_in, const T *curv_in, T *zn)
 {
     const T h = P.h;
+    const T u[2] = { u_in[0], u_in[1] }, curv[3] = { curv_in[0], curv_in[1], curv_in[2] };   // keep in registers
     Slip<T> sl = slip_of(P, u[1]);
     const AngleBase<T> ab = angle_base(sl, z0);
     T z[NZ], zs[NZ], k[NZ], kacc[NZ];
@@ -291,9 +301,10 @@ IGT_HD void rhs_tangent(const RhsJac<T> &J, const T (*Ts)[NSEED], T (*dk)[NSEED]
 // one MPC step with sensitivities w.r.t. the 6 seeds (ey, epsi, v, psi, a, df): S[7][6].
 // dF/dx = e_x, dF/dy = e_y, dF/ds = e_s (dK/ds == 0) complete the Jacobian.
 template <typename T>
-IGT_HDN void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u, const T *curv, T *zn, T (*S)[NSEED])
+IGT_HDN void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u_in, const T *curv_in, T *zn, T (*S)[NSEED])
 {
     const T h = P.h;
+    const T u[2] = { u_in[0], u_in[1] }, curv[3] = { curv_in[0], curv_in[1], curv_in[2] };   // keep in registers
     Slip<T> sl = slip_of(P, u[1]);
     const AngleBase<T> ab = angle_base(sl, z0);
     T z[NZ], zs[NZ], k[NZ], kacc[NZ];
@@ -578,8 +589,8 @@ IGT_HD constexpr int he_j(int e)
 template <typename T>
 struct NodeCtx {
     T curv[3], uprev[2], mu, alpha;
-    const double *obs;
-    int cur, second_order;
+    const double *obs, *x0p;
+    int cur, second_order, ls;
 };
 
 template <typename T>
@@ -673,15 +684,67 @@ IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
     for (int e = 0; e < NHE; e++) w.Hl(k, e) = H[sym11(he_i(e), he_j(e))];
 }
 
-// Node phase 3 (after the closed-loop rollout of a trial step): slack / multiplier update of the
-// rows of node k along the step actually taken (d w_k = new - old iterate), the fraction-to-boundary
-// test, and the node's share of the infeasibility and of the barrier sum at the new point.
-// Tr(k, .) = (sum |c + y|, sum log y, 1 if the boundary rule failed).
+// Closed-loop nonlinear rollout of candidate j of the line search (step alpha / 2^j) from the
+// current iterate into buffer cand_buf(cur, j): controls and states only; the rows of the trial
+// point are evaluated by node_phase3.  Tc(buffer, .) = (1 if the rollout stayed finite, cost).
 template <typename T>
-IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k)
+IGT_HD void rollout_item(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int j)
 {
-    const int N = P.N, b = c.cur, nb = 1 - c.cur;
-    const T mu = c.mu, alpha = c.alpha, tau = fmax(P.tau_min, T(1) - mu);
+    const int N = P.N, b = c.cur, nb = cand_buf(c.cur, j);
+    T alpha = c.alpha;
+    for (int i = 0; i < j; i++) alpha *= T(0.5);
+    T zn[NZ], upn[2] = { c.uprev[0], c.uprev[1] };
+    T J = T(0), su = T(0);
+    bool fail = false;
+#pragma unroll
+    for (int i = 0; i < NZ; i++) { zn[i] = T(c.x0p[i]); w.Z(nb, 0, i) = zn[i]; }
+    for (int k = 0; k < N; k++) {
+        T dw[NA];
+        if (k + 1 < N) {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) w.pf(w.L.oZ[b] + (k + 1) * NZ + i);
+            w.pf(w.L.oU[b] + (k + 1) * 2); w.pf(w.L.oU[b] + (k + 1) * 2 + 1);
+            w.pf(w.L.oKu + (k + 1) * 2); w.pf(w.L.oKu + (k + 1) * 2 + 1);
+#pragma unroll
+            for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + (k + 1) * 2 * NA + i);
+        }
+#pragma unroll
+        for (int i = 0; i < NZ; i++) dw[i] = zn[i] - w.Z(b, k, i);
+        if (k == 0) { dw[IPA] = T(0); dw[IPD] = T(0); }
+        else { dw[IPA] = upn[0] - w.U(b, k - 1, 0); dw[IPD] = upn[1] - w.U(b, k - 1, 1); }
+        T d0 = alpha * w.ku(k, 0), d1 = alpha * w.ku(k, 1);
+#pragma unroll
+        for (int i = 0; i < NA; i++) { d0 += w.KK(k, 0, i) * dw[i]; d1 += w.KK(k, 1, i) * dw[i]; }
+        T un[2] = { w.U(b, k, 0) + d0, w.U(b, k, 1) + d1 };
+        J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
+        su += un[0] * un[0] + un[1] * un[1];
+        w.U(nb, k, 0) = un[0]; w.U(nb, k, 1) = un[1];
+        w.Du(nb, k, 0) = d0; w.Du(nb, k, 1) = d1;
+        T zz[NZ];
+        rk4_step(P, zn, un, c.curv, zz);
+        bool fin = true;
+#pragma unroll
+        for (int i = 0; i < NZ; i++) { zn[i] = zz[i]; w.Z(nb, k + 1, i) = zz[i]; fin = fin && (zz[i] == zz[i]) && fabs(zz[i]) < T(1e15); }
+        if (!fin) { fail = true; break; }
+        upn[0] = un[0]; upn[1] = un[1];
+    }
+    J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
+    w.Tc(nb, 0) = fail ? T(0) : T(1);
+    w.Tc(nb, 1) = J + P.w_u * su;
+}
+
+// Node phase 3 (after the rollout of candidate j): slack / multiplier update of the rows of node k
+// along the step actually taken (d w_k = new - old iterate), the fraction-to-boundary test, and the
+// node's share of the infeasibility and of the barrier sum at the new point.
+// Tr(buffer, k, .) = (sum |c + y|, sum log y, 1 if the boundary rule failed).
+template <typename T>
+IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k, int j)
+{
+    const int N = P.N, b = c.cur, nb = cand_buf(c.cur, j);
+    if (w.Tc(nb, 0) == T(0)) return;                            // the rollout left the finite range
+    T alpha = c.alpha;
+    for (int i = 0; i < j; i++) alpha *= T(0.5);
+    const T mu = c.mu, tau = fmax(P.tau_min, T(1) - mu);
     T z[NZ], up[2], u[2], zn[NZ], upn[2], un[2], dw[NW];
     node_load(P, w, c, k, z, up, u);
 #pragma unroll
@@ -690,7 +753,7 @@ IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
     else { upn[0] = w.U(nb, k - 1, 0); upn[1] = w.U(nb, k - 1, 1); }
     if (k < N) { un[0] = w.U(nb, k, 0); un[1] = w.U(nb, k, 1); } else { un[0] = un[1] = T(0); }
     dw[IPA] = upn[0] - up[0]; dw[IPD] = upn[1] - up[1];
-    if (k < N) { dw[IUA] = w.Du(k, 0); dw[IUD] = w.Du(k, 1); } else { dw[IUA] = dw[IUD] = T(0); }
+    if (k < N) { dw[IUA] = w.Du(nb, k, 0); dw[IUD] = w.Du(nb, k, 1); } else { dw[IUA] = dw[IUD] = T(0); }
     const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]);
     const int o = row_off(N, P.n_cinf, k);
     bool fail = false;
@@ -713,7 +776,7 @@ IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
             th += fabs(cv + yn);
             lg.add(yn);
         });
-    w.Tr(k, 0) = th; w.Tr(k, 1) = fail ? T(0) : lg.total(); w.Tr(k, 2) = fail ? T(1) : T(0);
+    w.Tr(nb, k, 0) = th; w.Tr(nb, k, 1) = fail ? T(0) : lg.total(); w.Tr(nb, k, 2) = fail ? T(1) : T(0);
 }
 
 // ------------------------------------------------------------------ the solver ---------
@@ -723,6 +786,7 @@ struct Solver {
     Ws<T> w;
     T x0[NZ], uprev[2], curv[3], ctx[4];
     const double *obs;        // this problem's [N+1][2] forecast (AoS, read-only)
+    const double *x0p;        // this problem's x0[7] in the caller's array
     bool gt;                  // gt_mpc terminal cost
     T *mlp_scratch;           // [2][6][width] when gt (per-thread slab), else null
     int mlp_width;
@@ -853,7 +917,8 @@ struct Solver {
 
     IGT_HD void load_inputs(const ProbIO &io, long p, bool has_ctx)
     {
-        for (int i = 0; i < NZ; i++) x0[i] = T(io.x0[p * NZ + i]);
+        x0p = io.x0 + p * NZ;
+        for (int i = 0; i < NZ; i++) x0[i] = T(x0p[i]);
         uprev[0] = T(io.u_prev[p * 2]); uprev[1] = T(io.u_prev[p * 2 + 1]);
         for (int i = 0; i < 3; i++) curv[i] = T(io.curv[p * 3 + i]);
         obs = io.obs + p * (P.N + 1) * 2;
@@ -933,7 +998,7 @@ struct Solver {
         NodeCtx<T> c;
         c.curv[0] = curv[0]; c.curv[1] = curv[1]; c.curv[2] = curv[2];
         c.uprev[0] = uprev[0]; c.uprev[1] = uprev[1];
-        c.mu = mu; c.alpha = alpha; c.obs = obs; c.cur = cur; c.second_order = P.second_order;
+        c.mu = mu; c.alpha = alpha; c.obs = obs; c.x0p = x0p; c.cur = cur; c.second_order = P.second_order; c.ls = ls;
         return c;
     }
 
@@ -1195,84 +1260,41 @@ struct Solver {
         if (!done) backward_post();
     }
 
-    // closed-loop nonlinear rollout with step alpha from buffer cur into buffer 1-cur (controls and
-    // states only; the rows of the trial point are evaluated by node_phase3).  Sets trial_ok = false
-    // if the rollout left the finite range.
-    IGT_HD void forward_rollout()
+    // gather the results of candidate j (rollout_item + node_phase3): trial_ok, cost, infeasibility, barrier sum
+    IGT_HD void collect_trial(int j)
     {
-        const int N = P.N, b = cur, nb = 1 - cur;
-        T zn[NZ], upn[2] = { uprev[0], uprev[1] };
-        T J = T(0), su = T(0);
-        bool fail = false;
-#pragma unroll
-        for (int i = 0; i < NZ; i++) { zn[i] = x0[i]; w.Z(nb, 0, i) = zn[i]; }
-        for (int k = 0; k < N; k++) {
-            T dw[NA];
-            prefetch_stage(b, k + 1, false, false, true);
-#pragma unroll
-            for (int i = 0; i < NZ; i++) dw[i] = zn[i] - w.Z(b, k, i);
-            if (k == 0) { dw[IPA] = T(0); dw[IPD] = T(0); }
-            else { dw[IPA] = upn[0] - w.U(b, k - 1, 0); dw[IPD] = upn[1] - w.U(b, k - 1, 1); }
-            T d0 = alpha * w.ku(k, 0), d1 = alpha * w.ku(k, 1);
-#pragma unroll
-            for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dw[j]; d1 += w.KK(k, 1, j) * dw[j]; }
-            T un[2] = { w.U(b, k, 0) + d0, w.U(b, k, 1) + d1 };
-            J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
-            su += un[0] * un[0] + un[1] * un[1];
-            w.U(nb, k, 0) = un[0]; w.U(nb, k, 1) = un[1];
-            w.Du(k, 0) = d0; w.Du(k, 1) = d1;
-            T zz[NZ];
-            rk4_step(P, zn, un, curv, zz);
-            bool fin = true;
-#pragma unroll
-            for (int i = 0; i < NZ; i++) { zn[i] = zz[i]; w.Z(nb, k + 1, i) = zz[i]; fin = fin && (zz[i] == zz[i]) && fabs(zz[i]) < T(1e15); }
-            if (!fin) { fail = true; break; }
-            upn[0] = un[0]; upn[1] = un[1];
-        }
-        J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
-        trial_ok = !fail;
-        Jcand = J + P.w_u * su;
-    }
-
-    // gather the per-node results of node_phase3 of the trial point
-    IGT_HD void collect_trial()
-    {
+        const int nb = cand_buf(cur, j);
+        trial_ok = w.Tc(nb, 0) != T(0);
+        if (!trial_ok) return;
         T th = T(0), lg = T(0), bad = T(0);
-        for (int k = 0; k <= P.N; k++) { th += w.Tr(k, 0); lg += w.Tr(k, 1); bad += w.Tr(k, 2); }
-        thetacand = th; lgcand = lg;
+        for (int k = 0; k <= P.N; k++) { th += w.Tr(nb, k, 0); lg += w.Tr(nb, k, 1); bad += w.Tr(nb, k, 2); }
+        Jcand = w.Tc(nb, 1); thetacand = th; lgcand = lg;
         if (bad > T(0)) trial_ok = false;
     }
 
-    // one trial step by one thread (tests/hostsim; the kernels run node_phase3 CTA-wide)
-    IGT_HD void forward_trial()
+    // acceptance test of the collected candidate (needs tcand, its terminal value)
+    IGT_HD bool trial_passes() const
     {
-        forward_rollout();
-        if (!trial_ok) return;
-        const NodeCtx<T> c = node_ctx();
-        for (int k = 0; k <= P.N; k++) node_phase3(P, w, c, k);
-        collect_trial();
+        if (!trial_ok) return false;
+        T phin = Jcand - tcand.V - mu * lgcand;
+        return (phin == phin) && fabs(phin) < T(1e30) &&
+               (phin < phi - P.eps_phi * fabs(phi) || thetacand < thetacur * (T(1) - P.gamma_theta) ||
+                (thetacand <= P.theta_small && phin <= phi + fmax(P.eps_phi * fmax(T(1), fabs(phi)), phi_noise)));
     }
 
-    // acceptance test (needs tcand of the candidate's terminal state when trial_ok)
-    IGT_HD void finish_trial()
+    // close a batch of `tried` candidates alpha, alpha/2, ...: `jacc` >= 0 is the first that passed (the
+    // one sequential halving would have stopped at; collect_trial(jacc) is the last one collected)
+    IGT_HD void finish_trials(int jacc, int tried)
     {
-        bool accepted = false;
-        trials++;
-        if (trial_ok) {
-            T phin = Jcand - tcand.V - mu * lgcand;
-            accepted = (phin == phin) && fabs(phin) < T(1e30) &&
-                       (phin < phi - P.eps_phi * fabs(phi) || thetacand < thetacur * (T(1) - P.gamma_theta) ||
-                        (thetacand <= P.theta_small && phin <= phi + fmax(P.eps_phi * fmax(T(1), fabs(phi)), phi_noise)));
-        }
-        if (accepted) {
-            cur = 1 - cur;
+        if (jacc >= 0) {
+            cur = cand_buf(cur, jacc);
             Jcur = Jcand; lgcur = lgcand; thetacur = thetacand; tcur = tcand;
             reg = reg > P.reg_min ? reg / P.reg_down : T(0);
             need_back = 2;
             iters++;
         } else {
-            alpha *= T(0.5);
-            ls++;
+            for (int i = 0; i < tried; i++) alpha *= T(0.5);
+            ls += tried;
             if (ls >= P.n_alpha) {
                 reg = fmax(reg * P.reg_up, P.reg_min);
                 iters++;
@@ -1281,7 +1303,30 @@ struct Solver {
             }
         }
         // budget of forward passes, checked between iterations like the iteration cap
-        if (!done && (accepted || need_back == 1) && trials >= P.max_trials) { status = 1; done = true; }
+        if (!done && (jacc >= 0 || need_back == 1) && trials >= P.max_trials) { status = 1; done = true; }
+    }
+
+    // judge candidates 0 .. nj-1 in the order sequential halving would try them
+    IGT_HD void accept_trials(int nj)
+    {
+        int jacc = -1, tried = 0;
+        for (int j = 0; j < nj && jacc < 0; j++) {
+            trials++; tried++;
+            collect_trial(j);
+            if (trial_ok) terminal_of(cand_buf(cur, j), tcand, true);
+            if (trial_passes()) jacc = j;
+        }
+        finish_trials(jacc, tried);
+    }
+
+    // one candidate evaluated start to finish by one thread (tests/hostsim; the kernels run the
+    // rollouts and node_phase3 of all candidates CTA-wide, see trial_phase_cta)
+    IGT_HD void trial_serial()
+    {
+        const NodeCtx<T> c = node_ctx();
+        rollout_item(P, w, c, 0);
+        for (int k = 0; k <= P.N; k++) node_phase3(P, w, c, k, 0);
+        accept_trials(1);
     }
 
     // write the outputs of this problem (x, u, cost, max row violation in reference units)
@@ -1341,9 +1386,7 @@ IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, l
         while (!sv.done) {
             if (sv.need_back) sv.backward();
             if (sv.done) break;
-            sv.forward_trial();
-            if (sv.trial_ok) sv.terminal_of(1 - sv.cur, sv.tcand, true);
-            sv.finish_trial();
+            sv.trial_serial();
         }
     }
     sv.write_out(io, p);
@@ -1425,37 +1468,72 @@ struct NodeList {                    // shared-memory work list of one CTA-wide 
     NodeCtx<T> ctx[MAX_SOLVE_BLOCK];
 };
 
+// compact the problems of the CTA that need a phase into the shared work list (slot order is kept,
+// so that neighbouring lanes mostly work on neighbouring slots); returns their number
+template <typename T>
+__device__ __forceinline__ int cta_list_build(bool need, long bound, const Solver<T> &sv, NodeList<T> &nl)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const unsigned m = __ballot_sync(FULL, need);
+    if (lane == 0) nl.wcnt[warp] = __popc(m);
+    __syncthreads();
+    int base = 0, n = 0;
+    for (int i = 0; i < nw; i++) { int c = nl.wcnt[i]; if (i < warp) base += c; n += c; }
+    if (need) {
+        const int idx = base + __popc(m & ((1u << lane) - 1u));
+        nl.slot[idx] = (int)bound;
+        nl.ctx[idx] = sv.node_ctx();
+    }
+    __syncthreads();
+    return n;
+}
+
 template <typename T, int PHASE>
 __device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
                                                long bound, const Solver<T> &sv, NodeList<T> &nl)
 {
-    int *s_wcnt = nl.wcnt, *s_slot = nl.slot;
-    NodeCtx<T> *s_ctx = nl.ctx;
-    const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const unsigned m = __ballot_sync(FULL, need);
-    if (lane == 0) s_wcnt[warp] = __popc(m);
-    __syncthreads();
-    int base = 0, n = 0;
-    for (int i = 0; i < nw; i++) { int c = s_wcnt[i]; if (i < warp) base += c; n += c; }
-    if (need) {
-        const int idx = base + __popc(m & ((1u << lane) - 1u));
-        s_slot[idx] = (int)bound;
-        s_ctx[idx] = sv.node_ctx();
-    }
-    __syncthreads();
+    const int n = cta_list_build(need, bound, sv, nl);
     if (n > 0) {
         Ws<T> w; w.L = L;
         const int total = n * (P.N + 1);
-        for (int it = tid; it < total; it += blockDim.x) {
+        for (int it = threadIdx.x; it < total; it += blockDim.x) {
             const int j = it % n, k = it / n;
-            w.bind(ws_base, s_slot[j]);
-            if (PHASE == 1) node_phase1(P, w, s_ctx[j], k);
-            else if (PHASE == 2) node_phase2(P, w, s_ctx[j], k);
-            else node_phase3(P, w, s_ctx[j], k);
+            w.bind(ws_base, nl.slot[j]);
+            if (PHASE == 1) node_phase1(P, w, nl.ctx[j], k);
+            else node_phase2(P, w, nl.ctx[j], k);
         }
     }
     __syncthreads();
+}
+
+// CTA-wide trial phase with a speculative line search.  The candidates alpha, alpha/2, ... of one
+// line search are judged against the same reference point, so they are independent: when fewer
+// problems than threads are in their trial phase (the tail of a batch, small batches), the spare
+// threads roll out the next halvings at the same time, each into its own iterate buffer, and the
+// owner then takes the first candidate that passes -- the same iterate sequential halving reaches,
+// in one pass instead of up to n_alpha.  Returns the number of candidates per problem.
+template <typename T>
+__device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
+                                               long bound, const Solver<T> &sv, NodeList<T> &nl, bool speculate)
+{
+    const int n = cta_list_build(need, bound, sv, nl);
+    if (n == 0) return 1;                                         // CTA-uniform
+    int n_spec = 1;
+    if (speculate) { n_spec = (int)blockDim.x / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
+    Ws<T> w; w.L = L;
+    for (int it = threadIdx.x; it < n * n_spec; it += blockDim.x) {
+        const int q = it % n, j = it / n;
+        if (j < P.n_alpha - nl.ctx[q].ls) { w.bind(ws_base, nl.slot[q]); rollout_item(P, w, nl.ctx[q], j); }
+    }
+    __syncthreads();
+    const int total = n * n_spec * (P.N + 1);
+    for (int it = threadIdx.x; it < total; it += blockDim.x) {
+        const int q = it % n, r = it / n, j = r % n_spec, k = r / n_spec;
+        if (j < P.n_alpha - nl.ctx[q].ls) { w.bind(ws_base, nl.slot[q]); node_phase3(P, w, nl.ctx[q], k, j); }
+    }
+    __syncthreads();
+    return n_spec;
 }
 
 // Optional per-phase cycle counters of the first thread of CTA 0 (build with -DIGT_PHASE_CLOCKS;
@@ -1594,23 +1672,25 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         IGT_TICK(6);
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
-        if (trying) sv.forward_rollout();
+        const int n_spec = trial_phase_cta(P, ws_base, sv.w.L, trying, bound, sv, nl, !TC);
         IGT_TICK(7);
-        node_phase_cta<T, 3>(P, ws_base, sv.w.L, trying && sv.trial_ok, bound, sv, nl);
-        if (trying && sv.trial_ok) sv.collect_trial();
-        IGT_TICK(8);
         if (TC) {
+            // one candidate per pass; its terminal value comes from the tensor cores, CTA-wide
+            if (trying) { sv.trials++; sv.collect_trial(0); }
             const bool need = trying && sv.trial_ok;
             if (__syncthreads_or(need)) {
+                const int nb = cand_buf(sv.cur, 0);
                 float cx[4] = { float(sv.ctx[0]), float(sv.ctx[1]), float(sv.ctx[2]), float(sv.ctx[3]) }, o[6];
-                float sN = need ? float(sv.w.Z(1 - sv.cur, P.N, IS)) : 0.f, vN = need ? float(sv.w.Z(1 - sv.cur, P.N, IV)) : 0.f;
+                float sN = need ? float(sv.w.Z(nb, P.N, IS)) : 0.f, vN = need ? float(sv.w.Z(nb, P.N, IV)) : 0.f;
                 mlp_tc_eval(*tc, need, sN, vN, cx, o);
                 if (need) term_from_tc(o, sv.tcand);
             }
-        } else if (trying && sv.trial_ok) {
-            sv.terminal_of(1 - sv.cur, sv.tcand, true);
+            if (trying) sv.finish_trials(sv.trial_passes() ? 0 : -1, 1);
+        } else if (trying) {
+            const int left = P.n_alpha - sv.ls;
+            sv.accept_trials(n_spec < left ? n_spec : left);
         }
-        if (trying) sv.finish_trial();
+        IGT_TICK(8);
         if (active && sv.done) { sv.write_out(io, p); active = false; atomicSub(sc.in_flight, 1); }
         since_adopt++;
         IGT_TICK(10);

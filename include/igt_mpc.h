@@ -66,13 +66,13 @@ typedef struct {
     double reg_min, reg_up, reg_down, reg_max;
     double eps_phi, gamma_theta, theta_small;
     int max_iter;      /* mpc.py:137 uses 100*N for IPOPT */
-    int n_alpha;       /* step halvings per line search */
+    int n_alpha;       /* step halvings per line search (1..6: one iterate buffer per halving) */
     int second_order;  /* add the dt*Hess(lambda.f) curvature term to the Riccati pass */
     int stall_iter;    /* local-infeasibility exit: iteration >= stall_iter and ... */
     double stall_rp;   /* ... primal residual still above stall_rp -> IGT_STATUS_STALLED */
-    int max_trials;    /* budget of forward passes (accepted or not) per solve -> IGT_STATUS_MAXITER; a problem that
-                          burns all n_alpha halvings iteration after iteration is given up on (the reference's
-                          counterpart is IPOPT's max_wall_time, mpc.py:139) */
+    int max_trials;    /* optional budget of forward passes (accepted or not) per solve -> IGT_STATUS_MAXITER, for
+                          giving up early on problems that burn all n_alpha halvings iteration after iteration
+                          (the reference's counterpart is IPOPT's max_wall_time, mpc.py:139); 0 = no budget (default) */
     int precision;     /* IGT_PREC_F32 / IGT_PREC_F64: arithmetic of the solver kernels */
 } igt_params;
 

@@ -99,6 +99,8 @@ class COracle:
         for k, v in options.items():
             if not hasattr(cp, k):
                 raise KeyError(k)
+            if k == "max_trials" and v <= 0:       # igt_params convention: 0 = no budget of forward passes
+                v = 1000000
             setattr(cp, k, v)
         self.cp = cp
 

@@ -20,7 +20,9 @@ def main():
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     x0, up, cv, ob = t(x0), t(up), t(cv), t(ob)
     for prec in precs:
-        s = BatchSolver(N=N, precision=prec)
+        kw = {}
+        if os.environ.get('IGT_MAX_TRIALS'): kw['max_trials'] = int(os.environ['IGT_MAX_TRIALS'])
+        s = BatchSolver(N=N, precision=prec, **kw)
         out = s.solve_batch_device(x0, up, cv, ob); torch.cuda.synchronize()
         for _ in range(reps):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
