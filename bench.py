@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-closed-loop", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -247,6 +248,18 @@ def main():
     e2e_t, e2e_conv_all, _, _ = sharding.reduce_counters(e2e_t, e2e_conv, 0, 0, device=dev)
     e2e_value = e2e_conv_all * e2e_steps / e2e_t
 
+    # ---- p50 per-step solve latency of a closed-loop episode (second half of BASELINE.json's metric):
+    #      scenario 1, both vehicles per step (B = 2), 150 steps, host to host through solve_batch ----
+    cl_p50 = cl_p90 = None
+    if rank == 0 and mode == "mpc" and not args.no_closed_loop:
+        from igt_mpc_int_b200 import episode
+        spec = episode.reference_episode_specs(scenarios=[1])[:1]
+        cl_solver = solver if N == 40 else BatchSolver(N=40, precision=args.precision)
+        res = episode.run_closed_loop(cl_solver, spec, steps=150, N=40, record_latency=True)
+        cl_p50, cl_p90 = float(np.percentile(res.step_latency_ms, 50)), float(np.percentile(res.step_latency_ms, 90))
+        if cl_solver is not solver:
+            cl_solver.close()
+
     if rank == 0:
         # ---- rooflines ----
         peaks = {}
@@ -256,6 +269,13 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        traffic = None                                        # dram bytes per launch from the committed ncu capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tr.get("workload") == args.workload and tr.get("precision") == args.precision:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         kernel_ms = dev_ms / args.steps                       # solver + guess kernels of one step on this rank
         alg_bytes = 8.0 * (11 * N + 24) * B                   # 4(11N+24) B/solve for fp32 I/O; ours is fp64
         achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
@@ -270,10 +290,13 @@ def main():
                        "parallelism": "dp%d (independent problems, no data-path collective)" % world},
             "converged_fraction": conv_all / B_all, "mean_iterations": iters_all / B_all,
             "p50_step_latency_ms": float(np.median(step_ms)), "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
+            "closed_loop_step_latency_ms": {"p50": cl_p50, "p90": cl_p90,
+                                            "what": "scenario 1 episode, 150 steps, one B=2 solve per step (both vehicles), "
+                                                    "host to host incl. H2D/D2H, warm-started after step 0"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                          "note": "algorithmic bytes 8*(11N+24) per solve; the solver is CUDA-core/latency bound, "
                                  "see compute_roofline (SURVEY 8(d))"},
             "compute_roofline": {"bound": "%s-fma" % args.precision, "achieved": alg_flops / (kernel_ms * 1e-3) / 1e12,

@@ -184,9 +184,9 @@ IGT_HD void rot_small(double, double sa, double ca, double d, double *s, double 
         return;
     }
     double d2 = d * d, sd, cd;
-    if (fabs(d) <= 0.0625) {     // the usual case (drift within one 0.1 s step): d^13 / 13! < 4e-26
-        sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880 + d2 * (-1.0 / 39916800))))));
-        cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320 + d2 * (-1.0 / 3628800)))));
+    if (fabs(d) <= 0.0625) {     // the usual case (drift within one 0.1 s step): d^11 / 11! < 2e-21, d^10 / 10! < 3e-19
+        sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880)))));
+        cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320))));
     } else {
         sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880 + d2 * (-1.0 / 39916800 + d2 * (1.0 / 6227020800.0 + d2 * (-1.0 / 1307674368000.0))))))));
         cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320 + d2 * (-1.0 / 3628800 + d2 * (1.0 / 479001600.0 + d2 * (-1.0 / 87178291200.0)))))));

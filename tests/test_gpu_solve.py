@@ -159,3 +159,69 @@ def test_planner_protocol_matches_reference_interface(oracle_params):
     agents[0]['state'].v = 9.0
     pl.update_initial_condition(agents[0], Bag(a=0.1, df=0.0))
     assert pl.solve() == (None, None, False)
+
+
+def test_full_size_batch_properties(oracle_params):
+    """BASELINE config 2 at full size (32768 problems, N = 40), through properties that do not need
+    the oracle on every problem: (1) every converged solution satisfies the rows to 1e-6 and its
+    cost / violation are reproduced by the independent evaluation kernel; (2) a problem's result
+    does not depend on the batch it is solved in or on where it sits in it (persistent lanes, tail
+    hand-over, speculative line search and CTA-wide phases only re-order independent work): the
+    reversed batch and a 2048-problem slice give bit-identical results; (3) warm-starting from the
+    solution converges again to the same cost; (4) a 512-problem sample agrees with the oracle."""
+    from oracle import c_oracle
+    from igt_mpc_int_b200 import scenarios as S
+    B, N = 32768, 40
+    pb = S.mid_episode(B, N=N, seed=2026)
+    s = _solver(N)
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    ok = r["status"] == 0
+    assert ok.mean() > 0.9
+    assert np.max(r["viol"][ok]) <= 1e-6
+    idx = np.where(ok)[0][::16]
+    ev = s.evaluate(pb.x0[idx], pb.u_prev[idx], pb.curv[idx], pb.obs[idx], r["u"][idx])
+    assert np.max(relerr(ev["cost"], r["cost"][idx])) < 1e-9 and np.max(ev["viol"]) <= 1e-6
+    # (2) order / batch independence, bit for bit
+    rr = s.solve_batch(pb.x0[::-1], pb.u_prev[::-1], pb.curv[::-1], pb.obs[::-1])
+    for k in ("status", "iters", "cost", "u"):
+        assert np.array_equal(rr[k][::-1], r[k], equal_nan=True), k
+    sl = slice(5000, 7048)
+    rs = s.solve_batch(pb.x0[sl], pb.u_prev[sl], pb.curv[sl], pb.obs[sl])
+    for k in ("status", "iters", "cost", "u"):
+        assert np.array_equal(rs[k], r[k][sl], equal_nan=True), k
+    # (3) warm start from the solution
+    w = np.where(ok)[0][:4096]
+    rw = s.solve_batch(pb.x0[w], pb.u_prev[w], pb.curv[w], pb.obs[w], u_init=r["u"][w])
+    assert np.mean(rw["status"] == 0) > 0.995
+    okw = rw["status"] == 0
+    assert np.max(relerr(rw["cost"][okw], r["cost"][w][okw])) < 1e-4
+    assert np.median(rw["iters"][okw]) <= np.median(r["iters"][w]) 
+    # (4) oracle on a sample
+    smp = np.arange(0, B, 64)
+    o = c_oracle.COracle(oracle_params[N], max_iter=s.params.max_iter, max_trials=s.params.max_trials).solve(
+        pb.x0[smp], pb.u_prev[smp], pb.curv[smp], pb.obs[smp])
+    both = (o["status"] == 0) & (r["status"][smp] == 0)
+    assert np.mean((o["status"] == 0) == (r["status"][smp] == 0)) > 0.98
+    assert np.max(relerr(r["cost"][smp][both], o["cost"][both])) < 1e-4
+    assert np.max(np.abs(r["u"][smp][both] - o["U"][both])) < 1e-3
+    s.close()
+
+
+@pytest.mark.parametrize("N", [10, 20])
+def test_short_horizons_full_path(oracle_params, N):
+    """BASELINE config 5 horizons N = 10, 20 (N = 40 is covered above) on 4096 problems vs the oracle."""
+    from oracle import c_oracle
+    from igt_mpc_int_b200 import scenarios as S
+    B = 4096
+    pb = S.mid_episode(B, N=N, seed=5)
+    s = _solver(N)
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    o = c_oracle.COracle(oracle_params[N], max_iter=s.params.max_iter, max_trials=s.params.max_trials).solve(
+        pb.x0, pb.u_prev, pb.curv, pb.obs)
+    both = (o["status"] == 0) & (r["status"] == 0)
+    assert both.mean() > 0.85
+    assert np.mean((o["status"] == 0) == (r["status"] == 0)) > 0.99
+    assert np.max(relerr(r["cost"][both], o["cost"][both])) < 1e-4
+    assert np.max(np.abs(r["u"][both] - o["U"][both])) < 1e-3
+    assert np.max(r["viol"][both]) <= 1e-6
+    s.close()
