@@ -145,10 +145,27 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Print the one JSON line on the real stdout (fd 1 is pointed at stderr while the bench runs, so that
+    library chatter such as NCCL's version banner cannot end up next to it)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -315,7 +332,7 @@ def main():
                                     "sample": "first %d problems of the same batch, oracle fp64 C restatement on all "
                                               "host threads (the reference's CasADi/IPOPT solver is not installable "
                                               "offline)" % n_sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     solver.close()
     if world > 1:
         dist.barrier()
