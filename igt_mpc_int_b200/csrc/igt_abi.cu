@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(128) rollout_kernel(int B, const float *__rest
     for (int k = 0; k < N; k++) {
         float u[2] = { U[((long)p * N + k) * 2], U[((long)p * N + k) * 2 + 1] };
         if (A) {
-            float zn[NZ], S[NZ][NSEED];
-            rk4_step_sens(P, z, u, curv, zn, S);
+            float zn[NZ], Sc[NSENS], S[NZ][NSEED];
+            rk4_step_sens(P, z, u, curv, zn, Sc);
+            expand_sens(P, Sc, S);
             float *Ak = A + ((long)p * N + k) * NZ * NZ, *Bk = Bm + ((long)p * N + k) * NZ * 2;
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
@@ -93,26 +94,30 @@ __global__ void __launch_bounds__(128) rollout_kernel(int B, const float *__rest
                 Bk[i * 2] = S[i][4]; Bk[i * 2 + 1] = S[i][5];
             }
         }
-        // compensated value step
-        Slip<float> sl = slip_of(P, u[1]);
-        const AngleBase<float> ab = angle_base(sl, z);
+        // compensated value step: the same stage derivatives as rk4_core, Kahan-summed increments
+        const StepK<float> c = step_setup(P, z, u, curv);
         for (int it = 0; it < P.n_rk; it++) {
-            float zs[NZ], k1[NZ], k2[NZ], k3[NZ], k4[NZ];
-            rhs<float, false>(P, z, u[0], sl, ab, curv, k1, nullptr);
-#pragma unroll
-            for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * 0.5f * k1[i];
-            rhs<float, false>(P, zs, u[0], sl, ab, curv, k2, nullptr);
-#pragma unroll
-            for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * 0.5f * k2[i];
-            rhs<float, false>(P, zs, u[0], sl, ab, curv, k3, nullptr);
-#pragma unroll
-            for (int i = 0; i < NZ; i++) zs[i] = z[i] + h * k3[i];
-            zs[IPSI] = z[IPSI] + h * 0.5f * k3[IPSI];
-            rhs<float, false>(P, zs, u[0], sl, ab, curv, k4, nullptr);
+            Deriv<float> k1, k2, k3, k4;
+            RhsJac<float> J;
+            const float hh = 0.5f * h;
+            stage_deriv<float, false>(c, z[IS], z[IEY], z[IEPSI], z[IV], z[IPSI], k1, J);
+            stage_deriv<float, false>(c, z[IS] + hh * k1.s, z[IEY] + hh * k1.ey, z[IEPSI] + hh * k1.ep, z[IV] + hh * u[0],
+                                      z[IPSI] + hh * k1.ps, k2, J);
+            stage_deriv<float, false>(c, z[IS] + hh * k2.s, z[IEY] + hh * k2.ey, z[IEPSI] + hh * k2.ep, z[IV] + hh * u[0],
+                                      z[IPSI] + hh * k2.ps, k3, J);
+            stage_deriv<float, false>(c, z[IS] + h * k3.s, z[IEY] + h * k3.ey, z[IEPSI] + h * k3.ep, z[IV] + h * u[0],
+                                      z[IPSI] + hh * k3.ps, k4, J);      // psi + h/2 k3: the reference's k4 quirk
+            float inc[NZ];
+            inc[IX] = h / 6.f * (k1.x + 2.f * k2.x + 2.f * k3.x + k4.x);
+            inc[IY] = h / 6.f * (k1.y + 2.f * k2.y + 2.f * k3.y + k4.y);
+            inc[IS] = h / 6.f * (k1.s + 2.f * k2.s + 2.f * k3.s + k4.s);
+            inc[IEY] = h / 6.f * (k1.ey + 2.f * k2.ey + 2.f * k3.ey + k4.ey);
+            inc[IEPSI] = h / 6.f * (k1.ep + 2.f * k2.ep + 2.f * k3.ep + k4.ep);
+            inc[IV] = h * u[0];
+            inc[IPSI] = h / 6.f * (k1.ps + 2.f * k2.ps + 2.f * k3.ps + k4.ps);
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
-                float inc = h / 6.f * (k1[i] + 2.f * k2[i] + 2.f * k3[i] + k4[i]);
-                float y = inc - comp[i];
+                float y = inc[i] - comp[i];
                 float t = z[i] + y;
                 comp[i] = (t - z[i]) - y;
                 z[i] = t;
@@ -673,6 +678,21 @@ int igt_debug_phase_clocks(igt_handle *h, long long *out16)
     if (!h || !out16) return IGT_EINVAL;
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpyFromSymbol(out16, g_phase_clk, 16 * sizeof(long long)));
+    return IGT_OK;
+}
+int igt_debug_round_clocks(igt_handle *h, long long *clk512, int *n512)
+{
+    if (!h || !clk512 || !n512) return IGT_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(clk512, g_round_clk, 512 * sizeof(long long)));
+    CK(cudaMemcpyFromSymbol(n512, g_round_n, 512 * sizeof(int)));
+    return IGT_OK;
+}
+int igt_debug_round_phases(igt_handle *h, int *ph512x12)
+{
+    if (!h || !ph512x12) return IGT_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(ph512x12, g_round_ph, 512 * 12 * sizeof(int)));
     return IGT_OK;
 }
 #endif

@@ -31,9 +31,17 @@
 #define IGT_HDN
 #endif
 
+#ifndef IGT_PF_DIST
+#define IGT_PF_DIST 2          // stages ahead the latency-bound sweeps (adjoint, step bound) prefetch
+#endif
+#ifndef IGT_PF_DIST_R
+#define IGT_PF_DIST_R 1        // ... and the Riccati sweep (compute-bound: one stage ahead is enough)
+#endif
+
 namespace igt {
 
 constexpr int NZ = 7, NA = 9, NW = 11, NSEED = 6;
+constexpr int NSENS = 26;   // structural non-zeros of a stage's sensitivities, see rk4_core
 enum { IX = 0, IY, IS, IEY, IEPSI, IV, IPSI, IPA, IPD, IUA, IUD };
 constexpr int MAX_CINF = 128;
 // Node-local summaries of the inequality rows.  The rows of a node touch 8 entries of the gradient in
@@ -88,7 +96,7 @@ struct WsLayout {
         for (int b = 0; b < NBUF; b++) { oU[b] = o; o += 2 * N; }
         for (int b = 0; b < NBUF; b++) { oY[b] = o; o += M; }
         for (int b = 0; b < NBUF; b++) { oS[b] = o; o += M; }
-        oSens = o; o += NZ * NSEED * N;
+        oSens = o; o += NSENS * N;
         oLam = o;  o += NZ * (N + 1);
         oKu = o;   o += 2 * N;
         oKK = o;   o += 2 * NA * N;
@@ -123,7 +131,7 @@ struct Ws {
     IGT_HD T &U(int b, int k, int i) const { return at(L.oU[b] + k * 2 + i); }
     IGT_HD T &Y(int b, int r) const { return at(L.oY[b] + r); }
     IGT_HD T &S(int b, int r) const { return at(L.oS[b] + r); }
-    IGT_HD T &Sens(int k, int i, int j) const { return at(L.oSens + (k * NZ + i) * NSEED + j); }
+    IGT_HD T &Sens(int k, int e) const { return at(L.oSens + k * NSENS + e); }
     IGT_HD T &Lam(int k, int i) const { return at(L.oLam + k * NZ + i); }
     IGT_HD T &ku(int k, int i) const { return at(L.oKu + k * 2 + i); }
     IGT_HD T &KK(int k, int i, int j) const { return at(L.oKK + (k * 2 + i) * NA + j); }
@@ -152,7 +160,7 @@ struct Slip { T beta, dbeta, sb, cb; };
 
 template <typename T>
 IGT_HD Slip<T> slip_of(const DevParams<T> &P, T df)
-{   // kinematic_bicycle_model_frenet.py:72
+{   // kinematic_bicycle_model.py:26 (Cartesian Euler model only; the Frenet model uses step_setup)
     Slip<T> r;
     T t = tan(df);
     r.beta = atan(P.rho * t);
@@ -167,188 +175,250 @@ IGT_HD T curvature(T s, T b0, T b1, T kv)
     return (s >= b0 ? kv : T(0)) - (s >= b1 ? kv : T(0));
 }
 
-// sin/cos of (a + d) from sin/cos of a for the small within-step drift d of epsi and psi:
-// one MPC step evaluates the right-hand side 16 times at angles that differ from the step's
-// start by < 0.1 rad, so two full-range sincos per step plus 16 short polynomials replace 32
-// full-range fp64 sincos calls (40 % of all executed instructions in the first profile).
-// |d| <= 0.25: Taylor to d^15 / d^14, truncation error < 1e-20; beyond that the library path.
-template <typename T>
-struct AngleBase { T e0, p0, a1, a2, s1b, c1b, spb, cpb; };
-
-IGT_HD void rot_small(double, double sa, double ca, double d, double *s, double *c)
+// sin(d), cos(d) of the two small within-step drifts d1 = epsi - epsi_0 and d2 = psi - psi_0.
+// One MPC step evaluates the right-hand side 16 times at angles that differ from the step's start
+// by < 0.15 rad (yaw rate <= 1.4 rad/s), so two full-range sincos per step plus 16 short polynomial
+// pairs replace 32 full-range fp64 sincos calls.  Both drifts are evaluated in ONE straight-line
+// block (four independent Horner chains: the fp64 pipe issues one DFMA per ~2.2 cycles per warp but
+// a dependent DFMA waits ~9), Taylor to d^13 / d^14 with truncation error < 1e-21 for |d| <= 0.25;
+// beyond that (never seen in practice) the library is called.
+IGT_HD void sincos_small2(double d1, double d2, double &s1, double &c1, double &s2, double &c2)
 {
-    if (fabs(d) > 0.25) {
-        double sd, cd;
-        sincos(d, &sd, &cd);
-        *s = sa * cd + ca * sd; *c = ca * cd - sa * sd;
-        return;
-    }
-    double d2 = d * d, sd, cd;
-    if (fabs(d) <= 0.0625) {     // the usual case (drift within one 0.1 s step): d^11 / 11! < 2e-21, d^10 / 10! < 3e-19
-        sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880)))));
-        cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320))));
-    } else {
-        sd = d * (1.0 + d2 * (-1.0 / 6 + d2 * (1.0 / 120 + d2 * (-1.0 / 5040 + d2 * (1.0 / 362880 + d2 * (-1.0 / 39916800 + d2 * (1.0 / 6227020800.0 + d2 * (-1.0 / 1307674368000.0))))))));
-        cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24 + d2 * (-1.0 / 720 + d2 * (1.0 / 40320 + d2 * (-1.0 / 3628800 + d2 * (1.0 / 479001600.0 + d2 * (-1.0 / 87178291200.0)))))));
-    }
-    *s = sa * cd + ca * sd;
-    *c = ca * cd - sa * sd;
+    const double S1 = -1.0 / 6, S2 = 1.0 / 120, S3 = -1.0 / 5040, S4 = 1.0 / 362880, S5 = -1.0 / 39916800,
+                 S6 = 1.0 / 6227020800.0;
+    const double C1 = -0.5, C2 = 1.0 / 24, C3 = -1.0 / 720, C4 = 1.0 / 40320, C5 = -1.0 / 3628800,
+                 C6 = 1.0 / 479001600.0, C7 = -1.0 / 87178291200.0;
+    const double x1 = d1 * d1, x2 = d2 * d2;
+    double ps1 = S5 + x1 * S6, ps2 = S5 + x2 * S6, pc1 = C6 + x1 * C7, pc2 = C6 + x2 * C7;
+    ps1 = S4 + x1 * ps1; ps2 = S4 + x2 * ps2; pc1 = C5 + x1 * pc1; pc2 = C5 + x2 * pc2;
+    ps1 = S3 + x1 * ps1; ps2 = S3 + x2 * ps2; pc1 = C4 + x1 * pc1; pc2 = C4 + x2 * pc2;
+    ps1 = S2 + x1 * ps1; ps2 = S2 + x2 * ps2; pc1 = C3 + x1 * pc1; pc2 = C3 + x2 * pc2;
+    ps1 = S1 + x1 * ps1; ps2 = S1 + x2 * ps2; pc1 = C2 + x1 * pc1; pc2 = C2 + x2 * pc2;
+    pc1 = C1 + x1 * pc1; pc2 = C1 + x2 * pc2;
+    const double t1 = d1 * x1, t2 = d2 * x2;
+    s1 = d1 + t1 * ps1; s2 = d2 + t2 * ps2;
+    c1 = 1.0 + x1 * pc1; c2 = 1.0 + x2 * pc2;
+    if (fmax(fabs(d1), fabs(d2)) > 0.25) { sincos(d1, &s1, &c1); sincos(d2, &s2, &c2); }
 }
-IGT_HD void rot_small(float a, float, float, float d, float *s, float *c) { sincosf(a + d, s, c); }   // MUFU-fast already
-
-template <typename T>
-IGT_HD AngleBase<T> angle_base(const Slip<T> &sl, const T *z0)
-{
-    AngleBase<T> ab;
-    ab.e0 = z0[IEPSI]; ab.p0 = z0[IPSI];
-    ab.a1 = sl.beta + ab.e0; ab.a2 = ab.p0 + sl.beta;
-    sincos_t(ab.a1, &ab.s1b, &ab.c1b);
-    sincos_t(ab.a2, &ab.spb, &ab.cpb);
-    return ab;
+IGT_HD void sincos_small2(float d1, float d2, float &s1, float &c1, float &s2, float &c2)
+{   // fp32: terms to d^7 / d^8 (truncation < 2e-11 for |d| <= 0.25)
+    const float S1 = -1.f / 6, S2 = 1.f / 120, S3 = -1.f / 5040, C1 = -0.5f, C2 = 1.f / 24, C3 = -1.f / 720, C4 = 1.f / 40320;
+    const float x1 = d1 * d1, x2 = d2 * d2;
+    float ps1 = S2 + x1 * S3, ps2 = S2 + x2 * S3, pc1 = C3 + x1 * C4, pc2 = C3 + x2 * C4;
+    ps1 = S1 + x1 * ps1; ps2 = S1 + x2 * ps2; pc1 = C2 + x1 * pc1; pc2 = C2 + x2 * pc2;
+    pc1 = C1 + x1 * pc1; pc2 = C1 + x2 * pc2;
+    s1 = d1 + d1 * x1 * ps1; s2 = d2 + d2 * x2 * ps2;
+    c1 = 1.f + x1 * pc1; c2 = 1.f + x2 * pc2;
+    if (fmaxf(fabsf(d1), fabsf(d2)) > 0.25f) { sincosf(d1, &s1, &c1); sincosf(d2, &s2, &c2); }
 }
 
-// zdot (planner order) and, if JAC, the 13 state + 6 steering partials
+// Constants of one MPC step of the Frenet model (kinematic_bicycle_model_frenet.py:72): the slip angle
+// beta = atan(rho tan(df)) enters only through sin / cos, which follow from tan(df) algebraically, and
+// through beta + epsi, psi + beta, whose sin / cos at the step's start come from the angle-addition rule.
 template <typename T>
-struct RhsJac { T s_ey, s_epsi, s_v, s_d, ey_epsi, ey_v, ey_d, e_ey, e_epsi, e_v, e_d, x_v, x_psi, x_d, y_v, y_psi, y_d, p_v, p_d; };
+struct StepK {
+    T h, a, yawc, pdc, dbeta, sb, cb, tdf;   // yawc = sin(beta)/l_r, pdc = cos(beta)/l_r * dbeta/ddf
+    T e0, p0, s1b, c1b, spb, cpb;            // sin / cos of (beta + epsi_0) and (psi_0 + beta)
+    T b0, b1, kv;
+};
+
+template <typename T>
+IGT_HD StepK<T> step_setup(const DevParams<T> &P, const T *z0, const T *u, const T *curv)
+{
+    StepK<T> c;
+    c.h = P.h; c.a = u[0];
+    const T t = tan(u[1]), r = P.rho * t;
+    const T iq = T(1) / (T(1) + r * r);
+    c.tdf = t;
+    c.cb = sqrt(iq); c.sb = r * c.cb;
+    c.dbeta = P.rho * (T(1) + t * t) * iq;
+    c.yawc = c.sb * P.inv_lr;
+    c.pdc = c.cb * P.inv_lr * c.dbeta;
+    c.e0 = z0[IEPSI]; c.p0 = z0[IPSI];
+    T se, ce, sp, cp;
+    sincos_t(c.e0, &se, &ce);
+    sincos_t(c.p0, &sp, &cp);
+    c.s1b = se * c.cb + ce * c.sb; c.c1b = ce * c.cb - se * c.sb;
+    c.spb = sp * c.cb + cp * c.sb; c.cpb = cp * c.cb - sp * c.sb;
+    c.b0 = curv[0]; c.b1 = curv[1]; c.kv = curv[2];
+    return c;
+}
+
+// time derivative of (s, ey, epsi, x, y, psi) (v' = a) and, if JAC, its 13 state + 6 steering partials
+template <typename T>
+struct Deriv { T s, ey, ep, x, y, ps; };
+template <typename T>
+struct RhsJac { T s_ey, s_ep, s_v, s_d, ey_ep, ey_v, ey_d, e_ey, e_ep, e_v, e_d, x_v, x_ps, x_d, y_v, y_ps, y_d, p_v, p_d; };
 
 template <typename T, bool JAC>
-IGT_HD void rhs(const DevParams<T> &P, const T *z, T a, const Slip<T> &sl, const AngleBase<T> &ab, const T *curv, T *zd, RhsJac<T> *J)
+IGT_HD void stage_deriv(const StepK<T> &c, T s, T ey, T ep, T v, T ps, Deriv<T> &d, RhsJac<T> &J)
 {   // kinematic_bicycle_model_frenet.py:71-91
-    T ey = z[IEY], epsi = z[IEPSI], v = z[IV], psi = z[IPSI];
-    T K = curvature(z[IS], curv[0], curv[1], curv[2]);
-    T c1, s1, cp, sp;
-    rot_small(ab.a1, ab.s1b, ab.c1b, epsi - ab.e0, &s1, &c1);
-    rot_small(ab.a2, ab.spb, ab.cpb, psi - ab.p0, &sp, &cp);
-    T iden = (K == T(0)) ? T(1) : T(1) / (T(1) - K * ey);     // straight segments: no division
-    T sdot = v * c1 * iden;
-    T yaw = v * sl.sb * P.inv_lr;
-    zd[IS] = sdot;
-    zd[IEY] = v * s1;
-    zd[IEPSI] = yaw - sdot * K;
-    zd[IV] = a;
-    zd[IX] = v * cp;
-    zd[IY] = v * sp;
-    zd[IPSI] = yaw;
+    T s1, c1, sp, cp;
+    {
+        T sd1, cd1, sd2, cd2;
+        sincos_small2(ep - c.e0, ps - c.p0, sd1, cd1, sd2, cd2);
+        s1 = c.s1b * cd1 + c.c1b * sd1; c1 = c.c1b * cd1 - c.s1b * sd1;
+        sp = c.spb * cd2 + c.cpb * sd2; cp = c.cpb * cd2 - c.spb * sd2;
+    }
+    T K = T(0), iden = T(1);
+    if (c.kv != T(0)) {                                        // straight routes: no curvature test, no division
+        K = curvature(s, c.b0, c.b1, c.kv);
+        if (K != T(0)) iden = T(1) / (T(1) - K * ey);
+    }
+    const T sdot = v * c1 * iden;
+    const T yaw = v * c.yawc;
+    d.s = sdot;
+    d.ey = v * s1;
+    d.ep = yaw - sdot * K;
+    d.x = v * cp;
+    d.y = v * sp;
+    d.ps = yaw;
     if (JAC) {
-        T db = sl.dbeta;
-        J->s_ey = sdot * K * iden;
-        J->s_epsi = -v * s1 * iden;
-        J->s_v = c1 * iden;
-        J->s_d = J->s_epsi * db;
-        J->ey_epsi = v * c1; J->ey_v = s1; J->ey_d = v * c1 * db;
-        J->e_ey = -K * J->s_ey; J->e_epsi = -K * J->s_epsi;
-        J->e_v = sl.sb * P.inv_lr - K * J->s_v;
-        J->e_d = (v * sl.cb * P.inv_lr - K * J->s_epsi) * db;
-        J->x_v = cp; J->x_psi = -v * sp; J->x_d = -v * sp * db;
-        J->y_v = sp; J->y_psi = v * cp; J->y_d = v * cp * db;
-        J->p_v = sl.sb * P.inv_lr; J->p_d = v * sl.cb * P.inv_lr * db;
+        const T db = c.dbeta;
+        J.s_ey = sdot * K * iden;
+        J.s_ep = -v * s1 * iden;
+        J.s_v = c1 * iden;
+        J.s_d = J.s_ep * db;
+        J.ey_ep = v * c1; J.ey_v = s1; J.ey_d = J.ey_ep * db;
+        J.e_ey = -K * J.s_ey; J.e_ep = -K * J.s_ep;
+        J.e_v = c.yawc - K * J.s_v;
+        J.e_d = v * c.pdc - K * J.s_d;
+        J.x_v = cp; J.x_ps = -d.y; J.x_d = J.x_ps * db;
+        J.y_v = sp; J.y_ps = d.x; J.y_d = J.y_ps * db;
+        J.p_v = c.yawc; J.p_d = v * c.pdc;
     }
 }
 
-// one MPC step, values only.  k4 evaluates xdot, ydot at psi + h/2*k3[psi]
-// (kinematic_bicycle_model_frenet.py:111) -- reproduced on purpose.  The four stages run as a
-// loop (one copy of the right-hand side in the instruction stream, not sixteen).
+// Sensitivities of one MPC step, structural non-zeros only (26 of the 7 x 6 entries of
+// d z+ / d (ey, epsi, v, psi, a, df); d z+/d(x, y, s) = unit vectors since dK/ds == 0):
+//   rows x, y        w.r.t. (v, psi, a, df)        -- x, y follow v and psi only
+//   rows s, ey, epsi w.r.t. (ey, epsi, v, a, df)   -- psi feeds nothing but x, y
+//   row  psi         w.r.t. (v, a, df); d psi+/d psi = 1;  row v: d v+/d v = 1, d v+/d a = dt.
+enum { SX = 0, SY = 4, SS = 8, SEY = 13, SEP = 18, SPS = 23 };
+
+// One MPC step: n_rk RK4 sub-steps.  k4 evaluates xdot, ydot at psi + h/2*k3[psi]
+// (kinematic_bicycle_model_frenet.py:111) -- reproduced on purpose.  SENS adds the forward
+// sensitivities; the state arithmetic is the same expression for expression, so both variants
+// return bit-identical states (the solver relies on it: a trial point rolled out with or without
+// sensitivities is the same point).
+template <typename T, bool SENS>
+IGT_HD void rk4_core(const DevParams<T> &P, const T *z0, const T *u_in, const T *curv_in, T *zn, T *Sc)
+{
+    const StepK<T> c = step_setup(P, z0, u_in, curv_in);
+    const T h = c.h, hh = h * T(0.5), h6 = h / T(6), a = c.a;
+    const int n_rk = P.n_rk;
+    T x = z0[IX], y = z0[IY], s = z0[IS], ey = z0[IEY], ep = z0[IEPSI], v = z0[IV], ps = z0[IPSI];
+    // sensitivities of the rows that feed back (ey, epsi, psi): value at the sub-step's start;
+    // of the rows that do not (x, y, s): running sum of the weighted stage tangents over all sub-steps
+    T Sey[5], Sep[5], Sps[3], Ax[4], Ay[4], As[5];
+    if (SENS) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) { Sey[j] = T(0); Sep[j] = T(0); As[j] = T(0); }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { Ax[j] = T(0); Ay[j] = T(0); }
+        Sps[0] = Sps[1] = Sps[2] = T(0);
+        Sey[0] = T(1); Sep[1] = T(1);
+    }
+#pragma unroll 1
+    for (int it = 0; it < n_rk; it++) {
+        T ss = s, sey = ey, sep = ep, sv = v, sps = ps;           // stage state
+        T ks = T(0), key = T(0), kep = T(0), kx = T(0), ky = T(0), kps = T(0);
+        T Tey[5], Tep[5], Tps[3], Dey[5], Dep[5], Dps[3];        // stage tangents, weighted sums of this sub-step
+        const T tva0 = T(it) * h;                                 // d v / d a at the sub-step's start
+        if (SENS) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) { Tey[j] = Sey[j]; Tep[j] = Sep[j]; Dey[j] = T(0); Dep[j] = T(0); }
+#pragma unroll
+            for (int j = 0; j < 3; j++) { Tps[j] = Sps[j]; Dps[j] = T(0); }
+        }
+#pragma unroll
+        for (int st = 0; st < 4; st++) {
+            const T wgt = (st == 0 || st == 3) ? T(1) : T(2);
+            const T cf = (st == 2) ? h : hh;                      // step to the next stage's state; psi always moves by
+                                                                  // h/2, after k3 as well (the k4 quirk)
+            Deriv<T> d;
+            RhsJac<T> J;
+            stage_deriv<T, SENS>(c, ss, sey, sep, sv, sps, d, J);
+            ks += wgt * d.s; key += wgt * d.ey; kep += wgt * d.ep; kx += wgt * d.x; ky += wgt * d.y; kps += wgt * d.ps;
+            if (SENS) {
+                const T tva = st == 0 ? tva0 : (st == 3 ? tva0 + h : tva0 + hh);   // d v_stage / d a
+                T ds[5], dey[5], dep[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    ds[j] = J.s_ey * Tey[j] + J.s_ep * Tep[j];
+                    dey[j] = J.ey_ep * Tep[j];
+                    dep[j] = J.e_ey * Tey[j] + J.e_ep * Tep[j];
+                }
+                ds[2] += J.s_v; dey[2] += J.ey_v; dep[2] += J.e_v;
+                ds[3] += J.s_v * tva; dey[3] += J.ey_v * tva; dep[3] += J.e_v * tva;
+                ds[4] += J.s_d; dey[4] += J.ey_d; dep[4] += J.e_d;
+                const T dx[4] = { J.x_v + J.x_ps * Tps[0], J.x_ps, J.x_v * tva + J.x_ps * Tps[1], J.x_ps * Tps[2] + J.x_d };
+                const T dy[4] = { J.y_v + J.y_ps * Tps[0], J.y_ps, J.y_v * tva + J.y_ps * Tps[1], J.y_ps * Tps[2] + J.y_d };
+                const T dps[3] = { J.p_v, J.p_v * tva, J.p_d };
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    As[j] += wgt * ds[j]; Dey[j] += wgt * dey[j]; Dep[j] += wgt * dep[j];
+                    if (st < 3) { Tey[j] = Sey[j] + cf * dey[j]; Tep[j] = Sep[j] + cf * dep[j]; }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) { Ax[j] += wgt * dx[j]; Ay[j] += wgt * dy[j]; }
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    Dps[j] += wgt * dps[j];
+                    if (st < 3) Tps[j] = Sps[j] + hh * dps[j];
+                }
+            }
+            if (st < 3) {
+                ss = s + cf * d.s; sey = ey + cf * d.ey; sep = ep + cf * d.ep; sv = v + cf * a;
+                sps = ps + hh * d.ps;
+            }
+        }
+        x += h6 * kx; y += h6 * ky; s += h6 * ks; ey += h6 * key; ep += h6 * kep; ps += h6 * kps;
+        v += h6 * (a + T(2) * a + T(2) * a + a);
+        if (SENS) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) { Sey[j] += h6 * Dey[j]; Sep[j] += h6 * Dep[j]; }
+#pragma unroll
+            for (int j = 0; j < 3; j++) Sps[j] += h6 * Dps[j];
+        }
+    }
+    zn[IX] = x; zn[IY] = y; zn[IS] = s; zn[IEY] = ey; zn[IEPSI] = ep; zn[IV] = v; zn[IPSI] = ps;
+    if (SENS) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { Sc[SX + j] = h6 * Ax[j]; Sc[SY + j] = h6 * Ay[j]; }
+#pragma unroll
+        for (int j = 0; j < 5; j++) { Sc[SS + j] = h6 * As[j]; Sc[SEY + j] = Sey[j]; Sc[SEP + j] = Sep[j]; }
+#pragma unroll
+        for (int j = 0; j < 3; j++) Sc[SPS + j] = Sps[j];
+    }
+}
+
 template <typename T>
 IGT_HDN void rk4_step(const DevParams<T> &P, const T *z0, const T *u_in, const T *curv_in, T *zn)
 {
-    const T h = P.h;
-    const T u[2] = { u_in[0], u_in[1] }, curv[3] = { curv_in[0], curv_in[1], curv_in[2] };   // keep in registers
-    Slip<T> sl = slip_of(P, u[1]);
-    const AngleBase<T> ab = angle_base(sl, z0);
-    T z[NZ], zs[NZ], k[NZ], kacc[NZ];
-#pragma unroll
-    for (int i = 0; i < NZ; i++) z[i] = z0[i];
-#pragma unroll 1
-    for (int it = 0; it < P.n_rk; it++) {
-#pragma unroll
-        for (int i = 0; i < NZ; i++) { zs[i] = z[i]; kacc[i] = T(0); }
-#pragma unroll 1
-        for (int st = 0; st < 4; st++) {
-            rhs<T, false>(P, zs, u[0], sl, ab, curv, k, nullptr);
-            const T wgt = (st == 0 || st == 3) ? T(1) : T(2);
-            const T cf = (st == 2) ? T(1) : T(0.5);
-#pragma unroll
-            for (int i = 0; i < NZ; i++) { kacc[i] += wgt * k[i]; zs[i] = z[i] + h * cf * k[i]; }
-            if (st == 2) zs[IPSI] = z[IPSI] + h * T(0.5) * k[IPSI];
-        }
-#pragma unroll
-        for (int i = 0; i < NZ; i++) z[i] += h / T(6) * kacc[i];
-    }
-#pragma unroll
-    for (int i = 0; i < NZ; i++) zn[i] = z[i];
+    rk4_core<T, false>(P, z0, u_in, curv_in, zn, nullptr);
 }
 
-// tangent of one RHS evaluation: dk[7][6] from stage tangents Ts (rows ey, epsi, v, psi used)
+// one MPC step with its compact sensitivities Sc[NSENS]
 template <typename T>
-IGT_HD void rhs_tangent(const RhsJac<T> &J, const T (*Ts)[NSEED], T (*dk)[NSEED])
+IGT_HDN void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u_in, const T *curv_in, T *zn, T *Sc)
 {
-#pragma unroll
-    for (int j = 0; j < NSEED; j++) {
-        T tey = Ts[IEY][j], tep = Ts[IEPSI][j], tv = Ts[IV][j], tp = Ts[IPSI][j];
-        dk[IS][j] = J.s_ey * tey + J.s_epsi * tep + J.s_v * tv;
-        dk[IEY][j] = J.ey_epsi * tep + J.ey_v * tv;
-        dk[IEPSI][j] = J.e_ey * tey + J.e_epsi * tep + J.e_v * tv;
-        dk[IV][j] = T(0);
-        dk[IX][j] = J.x_v * tv + J.x_psi * tp;
-        dk[IY][j] = J.y_v * tv + J.y_psi * tp;
-        dk[IPSI][j] = J.p_v * tv;
-    }
-    dk[IV][4] = T(1);
-    dk[IS][5] += J.s_d; dk[IEY][5] += J.ey_d; dk[IEPSI][5] += J.e_d;
-    dk[IX][5] += J.x_d; dk[IY][5] += J.y_d; dk[IPSI][5] += J.p_d;
+    rk4_core<T, true>(P, z0, u_in, curv_in, zn, Sc);
 }
 
-// one MPC step with sensitivities w.r.t. the 6 seeds (ey, epsi, v, psi, a, df): S[7][6].
-// dF/dx = e_x, dF/dy = e_y, dF/ds = e_s (dK/ds == 0) complete the Jacobian.
+// dense d z+ / d (ey, epsi, v, psi, a, df) [7][6] from the compact form (ABI output, tests)
 template <typename T>
-IGT_HDN void rk4_step_sens(const DevParams<T> &P, const T *z0, const T *u_in, const T *curv_in, T *zn, T (*S)[NSEED])
+IGT_HD void expand_sens(const DevParams<T> &P, const T *Sc, T (*S)[NSEED])
 {
-    const T h = P.h;
-    const T u[2] = { u_in[0], u_in[1] }, curv[3] = { curv_in[0], curv_in[1], curv_in[2] };   // keep in registers
-    Slip<T> sl = slip_of(P, u[1]);
-    const AngleBase<T> ab = angle_base(sl, z0);
-    T z[NZ], zs[NZ], k[NZ], kacc[NZ];
-    T Ts[NZ][NSEED], dk[NZ][NSEED], dacc[NZ][NSEED];
-    RhsJac<T> J;
 #pragma unroll
-    for (int i = 0; i < NZ; i++) {
-        z[i] = z0[i];
+    for (int i = 0; i < NZ; i++)
 #pragma unroll
         for (int j = 0; j < NSEED; j++) S[i][j] = T(0);
-    }
-    S[IEY][0] = T(1); S[IEPSI][1] = T(1); S[IV][2] = T(1); S[IPSI][3] = T(1);
-#pragma unroll 1
-    for (int it = 0; it < P.n_rk; it++) {
-#pragma unroll
-        for (int i = 0; i < NZ; i++) {
-            zs[i] = z[i]; kacc[i] = T(0);
-#pragma unroll
-            for (int j = 0; j < NSEED; j++) { Ts[i][j] = S[i][j]; dacc[i][j] = T(0); }
-        }
-#pragma unroll 1
-        for (int st = 0; st < 4; st++) {
-            rhs<T, true>(P, zs, u[0], sl, ab, curv, k, &J);
-            rhs_tangent(J, Ts, dk);
-            const T wgt = (st == 0 || st == 3) ? T(1) : T(2);
-            const T cf = (st == 2) ? T(1) : T(0.5);
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                const T ci = (st == 2 && i == IPSI) ? T(0.5) : cf;      // the k4 psi quirk
-                kacc[i] += wgt * k[i];
-                zs[i] = z[i] + h * ci * k[i];
-#pragma unroll
-                for (int j = 0; j < NSEED; j++) { dacc[i][j] += wgt * dk[i][j]; Ts[i][j] = S[i][j] + h * ci * dk[i][j]; }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < NZ; i++) {
-            z[i] += h / T(6) * kacc[i];
-#pragma unroll
-            for (int j = 0; j < NSEED; j++) S[i][j] += h / T(6) * dacc[i][j];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NZ; i++) zn[i] = z[i];
+    const int c4[4] = { 2, 3, 4, 5 }, c5[5] = { 0, 1, 2, 4, 5 }, c3[3] = { 2, 4, 5 };
+    for (int j = 0; j < 4; j++) { S[IX][c4[j]] = Sc[SX + j]; S[IY][c4[j]] = Sc[SY + j]; }
+    for (int j = 0; j < 5; j++) { S[IS][c5[j]] = Sc[SS + j]; S[IEY][c5[j]] = Sc[SEY + j]; S[IEPSI][c5[j]] = Sc[SEP + j]; }
+    for (int j = 0; j < 3; j++) S[IPSI][c3[j]] = Sc[SPS + j];
+    S[IPSI][3] = T(1); S[IV][2] = T(1); S[IV][4] = P.dt;
 }
 
 // Cartesian Euler model, z = (x, y, psi, v): kinematic_bicycle_model.py:27-31
@@ -449,46 +519,86 @@ struct LogSum {
 
 // ------------------------------------------------------------------ rows ---------------
 // visit every inequality row of stage k (k == N: terminal node) in workspace order.
-// f(r, c, IC<i0>, g0, IC<i1>, g1, hxx, hxy, hyy): value, up to two gradient entries in
+// f(IC<slot>, r, c, IC<i0>, g0, IC<i1>, g1, hxx, hxy, hyy): value, up to two gradient entries in
 // w = (zeta, u) (i1 < 0: single entry), 2x2 Hessian block on (x, y) (collision row only).
-// The indices travel as types so that every use indexes registers statically.
+// The indices travel as types so that every use indexes registers statically.  `slot` is the row's
+// fixed register slot (0,1 speed; 2,3 ey; 4 collision; 5..12 input and rate rows), the same for every
+// stage, so that a node phase can load the slacks and multipliers of all rows of a node in one burst
+// (load_rows) before it computes -- a load issued per row between the stores of the previous row
+// exposes one memory latency per row.  The terminal-set rows of stage N-1 (slot -1) are visited only
+// if CINF; the node phases run them in their own chunked loops (cinf_chunks).
 template <int I> struct IC { static constexpr int value = I; };
+constexpr int NSLOT = 13;
+IGT_HD int slot_base(int N, int k) { return k == 0 ? 5 : (k == N ? 2 : 0); }      // workspace row = slot - base
+IGT_HD bool slot_used(int N, int k, int slot) { return k == 0 ? slot >= 5 : (k == N ? (slot >= 2 && slot <= 4) : true); }
 
-template <typename T, typename F>
+template <bool CINF = true, typename T, typename F>
 IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, const T *u, T ox, T oy, F &&f)
 {
     const T Z0 = T(0);
     int r = 0;
     if (k >= 1) {
         if (k < P.N) {
-            f(r++, z[IV] - P.v_max, IC<IV>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:317
-            f(r++, P.v_min - z[IV], IC<IV>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);     // mpc.py:316
+            f(IC<0>{}, r++, z[IV] - P.v_max, IC<IV>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:317
+            f(IC<1>{}, r++, P.v_min - z[IV], IC<IV>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);     // mpc.py:316
         }
-        f(r++, z[IEY] - P.ey_lim, IC<IEY>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:298
-        f(r++, -P.ey_lim - z[IEY], IC<IEY>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);    // mpc.py:299
+        f(IC<2>{}, r++, z[IEY] - P.ey_lim, IC<IEY>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:298
+        f(IC<3>{}, r++, -P.ey_lim - z[IEY], IC<IEY>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);    // mpc.py:299
         {   // mpc.py:226 in the equivalent distance form d_min - |p - o| <= 0
             T dx = z[IX] - ox, dy = z[IY] - oy;
             T dist = sqrt(dx * dx + dy * dy);
             dist = dist < T(1e-9) ? T(1e-9) : dist;
             T id = T(1) / dist, nx = dx * id, ny = dy * id;
-            f(r++, P.d_min - dist, IC<IX>{}, -nx, IC<IY>{}, -ny, -(T(1) - nx * nx) * id, nx * ny * id, -(T(1) - ny * ny) * id);
+            f(IC<4>{}, r++, P.d_min - dist, IC<IX>{}, -nx, IC<IY>{}, -ny, -(T(1) - nx * nx) * id, nx * ny * id, -(T(1) - ny * ny) * id);
         }
     }
     if (k == P.N) return;
-    f(r++, u[0] - P.a_max, IC<IUA>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);             // mpc.py:319
-    f(r++, P.a_min - u[0], IC<IUA>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:318
-    f(r++, u[1] - P.df_max, IC<IUD>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:321
-    f(r++, -P.df_max - u[1], IC<IUD>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);          // mpc.py:320
+    f(IC<5>{}, r++, u[0] - P.a_max, IC<IUA>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);             // mpc.py:319
+    f(IC<6>{}, r++, P.a_min - u[0], IC<IUA>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:318
+    f(IC<7>{}, r++, u[1] - P.df_max, IC<IUD>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:321
+    f(IC<8>{}, r++, -P.df_max - u[1], IC<IUD>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);          // mpc.py:320
     T da = u[0] - up[0], dd = u[1] - up[1];
-    f(r++, da - P.da_max, IC<IPA>{}, T(-1), IC<IUA>{}, T(1), Z0, Z0, Z0);          // mpc.py:303-311
-    f(r++, -da - P.da_max, IC<IPA>{}, T(1), IC<IUA>{}, T(-1), Z0, Z0, Z0);
-    f(r++, dd - P.ddf_max, IC<IPD>{}, T(-1), IC<IUD>{}, T(1), Z0, Z0, Z0);
-    f(r++, -dd - P.ddf_max, IC<IPD>{}, T(1), IC<IUD>{}, T(-1), Z0, Z0, Z0);
-    if (k == P.N - 1)
+    f(IC<9>{}, r++, da - P.da_max, IC<IPA>{}, T(-1), IC<IUA>{}, T(1), Z0, Z0, Z0);          // mpc.py:303-311
+    f(IC<10>{}, r++, -da - P.da_max, IC<IPA>{}, T(1), IC<IUA>{}, T(-1), Z0, Z0, Z0);
+    f(IC<11>{}, r++, dd - P.ddf_max, IC<IPD>{}, T(-1), IC<IUD>{}, T(1), Z0, Z0, Z0);
+    f(IC<12>{}, r++, -dd - P.ddf_max, IC<IPD>{}, T(1), IC<IUD>{}, T(-1), Z0, Z0, Z0);
+    if (CINF && k == P.N - 1)
 #pragma unroll 1
         for (int m = 0; m < P.n_cinf; m++)                                          // mpc.py:177-180
-            f(r++, P.cinf_A[m][0] * z[IV] + P.cinf_A[m][1] * u[0] - P.cinf_b[m], IC<IV>{}, P.cinf_A[m][0], IC<IUA>{},
+            f(IC<-1>{}, r++, P.cinf_A[m][0] * z[IV] + P.cinf_A[m][1] * u[0] - P.cinf_b[m], IC<IV>{}, P.cinf_A[m][0], IC<IUA>{},
               P.cinf_A[m][1], Z0, Z0, Z0);
+}
+
+// slacks (and multipliers) of the stage rows of node k of iterate buffer b, one burst of loads into
+// slot-indexed registers; o = row_off(N, n_cinf, k)
+template <bool WANT_S, typename T, typename W>
+IGT_HD void load_rows(const W &w, int N, int k, int b, int o, T *sv, T *yv)
+{
+    const int base = slot_base(N, k);
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; sl++)
+        if (slot_used(N, k, sl)) {
+            yv[sl] = w.Y(b, o + sl - base);
+            if (WANT_S) sv[sl] = w.S(b, o + sl - base);
+        }
+}
+
+// the terminal-set rows of stage N-1 (mpc.py:177-180; workspace rows o + 13 ...) in chunks of CCH: the
+// slacks and multipliers of a chunk are loaded in one burst, then f(m, r, s, y, A0, A1, b) runs per row
+constexpr int CCH = 8;
+template <typename T, typename W, typename F>
+IGT_HD void cinf_chunks(const DevParams<T> &P, const W &w, int b, int o, F &&f)
+{
+#pragma unroll 1
+    for (int m0 = 0; m0 < P.n_cinf; m0 += CCH) {
+        T s8[CCH], y8[CCH];
+#pragma unroll
+        for (int j = 0; j < CCH; j++)
+            if (m0 + j < P.n_cinf) { s8[j] = w.S(b, o + NSLOT + m0 + j); y8[j] = w.Y(b, o + NSLOT + m0 + j); }
+#pragma unroll
+        for (int j = 0; j < CCH; j++)
+            if (m0 + j < P.n_cinf) f(m0 + j, o + NSLOT + m0 + j, s8[j], y8[j], P.cinf_A[m0 + j][0], P.cinf_A[m0 + j][1], P.cinf_b[m0 + j]);
+    }
 }
 
 // symmetric 11x11 / 9x9 storage (upper triangle, row-major)
@@ -508,35 +618,40 @@ IGT_HD constexpr bool fmask(int a, int j)
            (a == IPA && j == IUA) || (a == IPD && j == IUD);
 }
 
-// build F[9][11] from the stored sensitivities S[7][6]
-template <typename T>
-IGT_HD void build_F(const DevParams<T> &P, const T (*S)[NSEED], T (*F)[NW])
+// F[9][11] = d zeta+ / d w of stage k from its stored compact sensitivities (see NSENS)
+template <typename T, typename W>
+IGT_HD void load_F(const DevParams<T> &P, const W &w, int k, T (*F)[NW])
 {
 #pragma unroll
     for (int a = 0; a < NA; a++)
 #pragma unroll
         for (int j = 0; j < NW; j++) F[a][j] = T(0);
-    F[IX][IX] = T(1); F[IY][IY] = T(1); F[IS][IS] = T(1);
-#pragma unroll
-    for (int a = 0; a < NZ; a++) {
-        F[a][IEY] = S[a][0]; F[a][IEPSI] = S[a][1]; F[a][IV] = S[a][2]; F[a][IPSI] = S[a][3];
-        F[a][IUA] = S[a][4]; F[a][IUD] = S[a][5];
-    }
+    F[IX][IX] = T(1); F[IY][IY] = T(1); F[IS][IS] = T(1); F[IV][IV] = T(1); F[IPSI][IPSI] = T(1);
     F[IPA][IUA] = T(1); F[IPD][IUD] = T(1);
+    F[IV][IUA] = P.dt;
+    F[IX][IV] = w.Sens(k, SX + 0); F[IX][IPSI] = w.Sens(k, SX + 1); F[IX][IUA] = w.Sens(k, SX + 2); F[IX][IUD] = w.Sens(k, SX + 3);
+    F[IY][IV] = w.Sens(k, SY + 0); F[IY][IPSI] = w.Sens(k, SY + 1); F[IY][IUA] = w.Sens(k, SY + 2); F[IY][IUD] = w.Sens(k, SY + 3);
+    F[IS][IEY] = w.Sens(k, SS + 0); F[IS][IEPSI] = w.Sens(k, SS + 1); F[IS][IV] = w.Sens(k, SS + 2);
+    F[IS][IUA] = w.Sens(k, SS + 3); F[IS][IUD] = w.Sens(k, SS + 4);
+    F[IEY][IEY] = w.Sens(k, SEY + 0); F[IEY][IEPSI] = w.Sens(k, SEY + 1); F[IEY][IV] = w.Sens(k, SEY + 2);
+    F[IEY][IUA] = w.Sens(k, SEY + 3); F[IEY][IUD] = w.Sens(k, SEY + 4);
+    F[IEPSI][IEY] = w.Sens(k, SEP + 0); F[IEPSI][IEPSI] = w.Sens(k, SEP + 1); F[IEPSI][IV] = w.Sens(k, SEP + 2);
+    F[IEPSI][IUA] = w.Sens(k, SEP + 3); F[IEPSI][IUD] = w.Sens(k, SEP + 4);
+    F[IPSI][IV] = w.Sens(k, SPS + 0); F[IPSI][IUA] = w.Sens(k, SPS + 1); F[IPSI][IUD] = w.Sens(k, SPS + 2);
 }
 
 // dt * Hess(lambda . f) on (ey, epsi, v, psi, df), added into the symmetric w-space Hessian
 template <typename T>
-IGT_HD void add_dyn_hessian(const DevParams<T> &P, const T *z, T df, const T *curv, const T *lam, T *H)
+IGT_HD void add_dyn_hessian(const DevParams<T> &P, const T *z, const T *u, const T *curv, const T *lam, T *H)
 {
-    T ey = z[IEY], epsi = z[IEPSI], v = z[IV], psi = z[IPSI];
+    const StepK<T> c = step_setup(P, z, u, curv);               // sin / cos of beta, beta + epsi, psi + beta
+    T ey = z[IEY], v = z[IV];
     T K = curvature(z[IS], curv[0], curv[1], curv[2]);
-    T t = tan(df), rho = P.rho;
-    T beta = atan(rho * t), q = T(1) + rho * rho * t * t;
-    T b1 = rho * (T(1) + t * t) / q;
+    T t = c.tdf, rho = P.rho;
+    T q = T(1) + rho * rho * t * t;
+    T b1 = c.dbeta;
     T b2 = rho * T(2) * t * (T(1) - rho * rho) / (q * q) * (T(1) + t * t);
-    T th = beta + epsi, ph = psi + beta;
-    T cth = cos(th), sth = sin(th), cph = cos(ph), sph = sin(ph), cb = cos(beta), sb = sin(beta);
+    T cth = c.c1b, sth = c.s1b, cph = c.cpb, sph = c.spb, cb = c.cb, sb = c.sb;
     T iD = T(1) / (T(1) - K * ey);
     T m = lam[IS] - K * lam[IEPSI], n = (lam[IEPSI] + lam[IPSI]) * P.inv_lr;
     T ley = lam[IEY], lx = lam[IX], ly = lam[IY];
@@ -614,21 +729,21 @@ IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
     T z[NZ], up[2], u[2];
     node_load(P, w, c, k, z, up, u);
     if (k < N) {
-        T zn[NZ], S[NZ][NSEED];
-        rk4_step_sens(P, z, u, c.curv, zn, S);
+        T zn[NZ], Sc[NSENS];
+        rk4_step_sens(P, z, u, c.curv, zn, Sc);
 #pragma unroll
-        for (int i = 0; i < NZ; i++)
-#pragma unroll
-            for (int j = 0; j < NSEED; j++) w.Sens(k, i, j) = S[i][j];
+        for (int e = 0; e < NSENS; e++) w.Sens(k, e) = Sc[e];
     }
     T gw[NW];
 #pragma unroll
     for (int i = 0; i < NW; i++) gw[i] = T(0);
     T rp = T(0), s_max = T(0), sy_min = T(1e30), sy_max = T(0);
     const int o = row_off(N, P.n_cinf, k);
-    visit_rows(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
-        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-        T s = w.S(b, o + r), y = w.Y(b, o + r);
+    T sv[NSLOT], yv[NSLOT];
+    load_rows<true>(w, N, k, b, o, sv, yv);
+    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto SL, int, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
+        constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        const T s = sv[sl], y = yv[sl];
         gw[i0] += g0 * s;
         if constexpr (i1 >= 0) gw[i1] += g1 * s;
         rp = fmax(rp, fabs(cv + y));
@@ -636,6 +751,15 @@ IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
         T sy = s * y;
         sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
     });
+    if (k == N - 1)
+        cinf_chunks(P, w, b, o, [&](int, int, T s, T y, T A0, T A1, T bb) {
+            const T cv = A0 * z[IV] + A1 * u[0] - bb;
+            gw[IV] += A0 * s; gw[IUA] += A1 * s;
+            rp = fmax(rp, fabs(cv + y));
+            s_max = fmax(s_max, s);
+            T sy = s * y;
+            sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
+        });
 #pragma unroll
     for (int e = 0; e < NGE; e++) w.Gw(k, e) = gw[ge_idx(e)];
     w.Red(k, 0) = rp; w.Red(k, 1) = s_max; w.Red(k, 2) = sy_min; w.Red(k, 3) = sy_max;
@@ -660,12 +784,14 @@ IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
         T ln[NZ];
 #pragma unroll
         for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
-        add_dyn_hessian(P, z, u[1], c.curv, ln, H);
+        add_dyn_hessian(P, z, u, c.curv, ln, H);
     }
     const int o = row_off(N, P.n_cinf, k);
-    visit_rows(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](int r, T cv, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
-        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-        T s = w.S(b, o + r), y = w.Y(b, o + r);
+    T sv[NSLOT], yv[NSLOT];
+    load_rows<true>(w, N, k, b, o, sv, yv);
+    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto SL, int, T cv, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
+        constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        const T s = sv[sl], y = yv[sl];
         T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
         g[i0] += g0 * gr;
         H[sym11(i0, i0)] += sig * g0 * g0;
@@ -678,6 +804,16 @@ IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
             H[sym11(IX, IX)] += s * hxx; H[sym11(IX, IY)] += s * hxy; H[sym11(IY, IY)] += s * hyy;
         }
     });
+    if (k == N - 1)
+        cinf_chunks(P, w, b, o, [&](int, int, T s, T y, T A0, T A1, T bb) {
+            const T cv = A0 * z[IV] + A1 * u[0] - bb;
+            T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
+            g[IV] += A0 * gr;
+            H[sym11(IV, IV)] += sig * A0 * A0;
+            g[IUA] += A1 * gr;
+            H[sym11(IUA, IUA)] += sig * A1 * A1;
+            H[sym11(IV, IUA)] += sig * A0 * A1;
+        });
 #pragma unroll
     for (int e = 0; e < NGE; e++) w.Gl(k, e) = g[ge_idx(e)];
 #pragma unroll
@@ -757,24 +893,41 @@ IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
     const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]);
     const int o = row_off(N, P.n_cinf, k);
     bool fail = false;
-    visit_rows(P, k, z, up, u, ox, oy, [&](int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
-        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-        T s = w.S(b, o + r), y = w.Y(b, o + r);
+    T sv[NSLOT], yv[NSLOT], ynv[NSLOT];
+    load_rows<true>(w, N, k, b, o, sv, yv);
+    visit_rows<false>(P, k, z, up, u, ox, oy, [&](auto SL, int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
+        constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        const T s = sv[sl], y = yv[sl];
         T dc = g0 * dw[i0];
         if constexpr (i1 >= 0) dc += g1 * dw[i1];
         T yn = y - alpha * (cv + y) - dc;
         T sn = s + (alpha * (s * cv + mu) + s * dc) / y;
         if (yn < (T(1) - tau) * y) fail = true;                 // fraction to the boundary
         sn = fmax(sn, (T(1) - tau) * s);                        // multiplier safeguard
+        ynv[sl] = yn;
         w.Y(nb, o + r) = yn; w.S(nb, o + r) = sn;
     });
+    // infeasibility and barrier sum at the trial point: the stage rows first, then (stage N-1) the
+    // terminal-set rows, whose update along the step and value at the new point share one loop
     T th = T(0);
     LogSum<T> lg;
     if (!fail)
-        visit_rows(P, k, zn, upn, un, ox, oy, [&](int r, T cv, auto, T, auto, T, T, T, T) {
-            T yn = w.Y(nb, o + r);
-            th += fabs(cv + yn);
-            lg.add(yn);
+        visit_rows<false>(P, k, zn, upn, un, ox, oy, [&](auto SL, int, T cv, auto, T, auto, T, T, T, T) {
+            constexpr int sl = decltype(SL)::value;
+            th += fabs(cv + ynv[sl]);
+            lg.add(ynv[sl]);
+        });
+    if (k == N - 1)
+        cinf_chunks(P, w, b, o, [&](int, int r, T s, T y, T A0, T A1, T bb) {
+            const T cv = A0 * z[IV] + A1 * u[0] - bb;
+            T dc = A0 * dw[IV];
+            dc += A1 * dw[IUA];
+            T yn = y - alpha * (cv + y) - dc;
+            T sn = s + (alpha * (s * cv + mu) + s * dc) / y;
+            if (yn < (T(1) - tau) * y) fail = true;
+            sn = fmax(sn, (T(1) - tau) * s);
+            w.Y(nb, r) = yn; w.S(nb, r) = sn;
+            if (!fail) { th += fabs(A0 * zn[IV] + A1 * un[0] - bb + yn); lg.add(yn); }
         });
     w.Tr(nb, k, 0) = th; w.Tr(nb, k, 1) = fail ? T(0) : lg.total(); w.Tr(nb, k, 2) = fail ? T(1) : T(0);
 }
@@ -831,7 +984,7 @@ struct Solver {
         }
         if (sens && k < P.N) {
 #pragma unroll
-            for (int i = 0; i < NZ * NSEED; i++) w.pf(w.L.oSens + k * NZ * NSEED + i);
+            for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
 #pragma unroll
             for (int i = 0; i < NZ; i++) w.pf(w.L.oLam + (k + 1) * NZ + i);
         }
@@ -842,12 +995,30 @@ struct Solver {
         }
     }
 
+    // stage k of the step-bound sweep: iterate, slacks (not the multipliers), sensitivities, gains
+    IGT_HD void prefetch_bound(int b, int k) const
+    {
+        if (k > P.N) return;
+#pragma unroll
+        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ[b] + k * NZ + i);
+        const int o = row_off(P.N, P.n_cinf, k);
+        const int n = (k == 0) ? 8 : (k == P.N ? 3 : 13);
+        for (int r = 0; r < n; r++) w.pf(w.L.oY[b] + o + r);
+        if (k == P.N) return;
+        w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1);
+        w.pf(w.L.oKu + k * 2); w.pf(w.L.oKu + k * 2 + 1);
+#pragma unroll
+        for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
+#pragma unroll
+        for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + k * 2 * NA + i);
+    }
+
     // next stage of the backward sweeps: sensitivities, node summaries, the few iterate entries used
     IGT_HD void prefetch_back(int b, int k, bool riccati) const
     {
         if (k < 0) return;
 #pragma unroll
-        for (int i = 0; i < NZ * NSEED; i++) w.pf(w.L.oSens + k * NZ * NSEED + i);
+        for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
         w.pf(w.L.oZ[b] + k * NZ + IEY); w.pf(w.L.oZ[b] + k * NZ + IEPSI);
         w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1);
         if (riccati) {
@@ -975,7 +1146,7 @@ struct Solver {
             if (k < N) { u[0] = w.U(0, k, 0); u[1] = w.U(0, k, 1); su += u[0] * u[0] + u[1] * u[1]; }
             J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
             int o = row_off(N, P.n_cinf, k);
-            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto, T, auto, T, T, T, T) {
+            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](auto, int r, T c, auto, T, auto, T, T, T, T) {
                 T y = fmax(-c, y_min);
                 w.Y(0, o + r) = y;
                 w.S(0, o + r) = mu / y;
@@ -1010,7 +1181,7 @@ struct Solver {
         stat = T(0); rp = T(0); s_max = T(0); sy_min = T(1e30); sy_max = T(0);
         for (int k = N; k >= 0; k--) {
             T gw[NW];
-            prefetch_back(b, k - 1, false);
+            prefetch_back(b, k - IGT_PF_DIST, false);
 #pragma unroll
             for (int i = 0; i < NW; i++) gw[i] = T(0);
 #pragma unroll
@@ -1023,12 +1194,8 @@ struct Solver {
                 for (int i = 0; i < NA; i++) lam[i] = gw[i];
                 lam[IS] -= tcur.gs; lam[IV] -= tcur.gv;
             } else {
-                T S[NZ][NSEED], F[NA][NW];
-#pragma unroll
-                for (int i = 0; i < NZ; i++)
-#pragma unroll
-                    for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
-                build_F(P, S, F);
+                T F[NA][NW];
+                load_F(P, w, k, F);
                 T ln[NA];
 #pragma unroll
                 for (int i = 0; i < NA; i++) ln[i] = lam[i];
@@ -1097,13 +1264,9 @@ struct Solver {
             Vxx[sym9(IS, IS)] -= tcur.Hss; Vxx[sym9(IS, IV)] -= tcur.Hsv; Vxx[sym9(IV, IV)] -= tcur.Hvv;
         }
         for (int k = N - 1; k >= 0; k--) {
-            T S[NZ][NSEED], F[NA][NW];
-            prefetch_back(b, k - 1, true);
-#pragma unroll
-            for (int i = 0; i < NZ; i++)
-#pragma unroll
-                for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
-            build_F(P, S, F);
+            T F[NA][NW];
+            prefetch_back(b, k - IGT_PF_DIST_R, true);
+            load_F(P, w, k, F);
             T g[NW], H[66];
             // g = F' Vx,  H = F' Vxx F   (structural zeros skipped at compile time)
             T VF[NA][NW];
@@ -1181,7 +1344,7 @@ struct Solver {
         for (int i = 0; i < NA; i++) dz[i] = T(0);
         for (int k = 0; k <= N; k++) {
             T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
-            prefetch_stage(b, k + 1, true, true, true);
+            prefetch_bound(b, k + IGT_PF_DIST);
             load_z(b, k, z); load_up(b, k, up);
 #pragma unroll
             for (int i = 0; i < NA; i++) dw[i] = dz[i];
@@ -1194,7 +1357,7 @@ struct Solver {
                 dw[IUA] = d0; dw[IUD] = d1;
             }
             int o = row_off(N, P.n_cinf, k);
-            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
+            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](auto, int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
                 constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
                 T y = w.Y(b, o + r);
                 T dc = g0 * dw[i0];
@@ -1203,12 +1366,8 @@ struct Solver {
                 if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
             });
             if (k == N) break;
-            T S[NZ][NSEED], F[NA][NW];
-#pragma unroll
-            for (int i = 0; i < NZ; i++)
-#pragma unroll
-                for (int j = 0; j < NSEED; j++) S[i][j] = w.Sens(k, i, j);
-            build_F(P, S, F);
+            T F[NA][NW];
+            load_F(P, w, k, F);
 #pragma unroll
             for (int i = 0; i < NA; i++) {
                 T acc = T(0);
@@ -1507,6 +1666,13 @@ __device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base
     __syncthreads();
 }
 
+#ifdef IGT_PHASE_CLOCKS
+__device__ long long g_mid_t;            // debug: end of the rollouts of CTA 0's last trial phase
+#define IGT_MID_TICK() do { if (blockIdx.x == 0 && threadIdx.x == 0) g_mid_t = clock64(); } while (0)
+#else
+#define IGT_MID_TICK() do { } while (0)
+#endif
+
 // CTA-wide trial phase with a speculative line search.  The candidates alpha, alpha/2, ... of one
 // line search are judged against the same reference point, so they are independent: when fewer
 // problems than threads are in their trial phase (the tail of a batch, small batches), the spare
@@ -1518,7 +1684,7 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
                                                long bound, const Solver<T> &sv, NodeList<T> &nl, bool speculate)
 {
     const int n = cta_list_build(need, bound, sv, nl);
-    if (n == 0) return 1;                                         // CTA-uniform
+    if (n == 0) { IGT_MID_TICK(); return 1; }                     // CTA-uniform
     int n_spec = 1;
     if (speculate) { n_spec = (int)blockDim.x / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
     Ws<T> w; w.L = L;
@@ -1527,6 +1693,7 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
         if (j < P.n_alpha - nl.ctx[q].ls) { w.bind(ws_base, nl.slot[q]); rollout_item(P, w, nl.ctx[q], j); }
     }
     __syncthreads();
+    IGT_MID_TICK();
     const int total = n * n_spec * (P.N + 1);
     for (int it = threadIdx.x; it < total; it += blockDim.x) {
         const int q = it % n, r = it / n, j = r % n_spec, k = r / n_spec;
@@ -1540,7 +1707,10 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
 // tools/phase_clocks.py reads them through igt_debug_phase_clocks).
 #ifdef IGT_PHASE_CLOCKS
 __device__ long long g_phase_clk[16];
-#define IGT_TICK(i) do { if (clk_on) { long long t_ = clock64(); clk[i] += t_ - clk_t; clk_t = t_; } } while (0)
+__device__ long long g_round_clk[512];   // per loop pass of CTA 0: cycles, and the number of its active problems
+__device__ int g_round_n[512];
+__device__ int g_round_ph[512][12];      // per loop pass: kcycles per phase
+#define IGT_TICK(i) do { if (clk_on) { long long t_ = clock64(); clk[i] += t_ - clk_t; if (round_i < 512) g_round_ph[round_i][i] += (int)((t_ - clk_t) >> 10); clk_t = t_; } } while (0)
 #else
 #define IGT_TICK(i) do { } while (0)
 #endif
@@ -1566,7 +1736,9 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
     if (TC) sv.phi_noise = T(3e-7);
 #ifdef IGT_PHASE_CLOCKS
     const bool clk_on = blockIdx.x == 0 && threadIdx.x == 0;
-    long long clk[16] = { 0 }, clk_t = clock64();
+    long long clk[16] = { 0 }, clk_t = clock64(), round_t = clk_t;
+    int round_i = 0;
+    if (clk_on) for (int i = 0; i < 12; i++) g_round_ph[0][i] = 0;
 #endif
     // All warps of the CTA (one CTA per SM) walk the phases together -- scheduling, backward
     // sweeps, forward trial -- separated by CTA barriers, so that the SM's instruction cache
@@ -1642,7 +1814,16 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
                 if (n > 0) since_adopt = 0;
             }
         }
+#ifdef IGT_PHASE_CLOCKS
+        const int cta_busy = __syncthreads_count(active);
+        if (clk_on && round_i < 512) {
+            long long t_ = clock64();
+            g_round_clk[round_i] = t_ - round_t; g_round_n[round_i] = cta_busy; round_t = t_; round_i++;
+            if (round_i < 512) for (int i = 0; i < 12; i++) g_round_ph[round_i][i] = 0;
+        }
+#else
         const int cta_busy = __syncthreads_or(active);
+#endif
         if (__syncthreads_and(wants_exit)) break;
         if (!cta_busy) { __nanosleep(2000); since_adopt++; IGT_TICK(9); continue; }   // nothing to do here: poll the queue gently
         IGT_TICK(0);
@@ -1673,7 +1854,10 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
         const int n_spec = trial_phase_cta(P, ws_base, sv.w.L, trying, bound, sv, nl, !TC);
-        IGT_TICK(7);
+#ifdef IGT_PHASE_CLOCKS
+        if (clk_on) { long long m_ = g_mid_t; clk[7] += m_ - clk_t; if (round_i < 512) g_round_ph[round_i][7] += (int)((m_ - clk_t) >> 10); clk_t = m_; }
+#endif
+        IGT_TICK(11);
         if (TC) {
             // one candidate per pass; its terminal value comes from the tensor cores, CTA-wide
             if (trying) { sv.trials++; sv.collect_trial(0); }
@@ -1696,7 +1880,10 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         IGT_TICK(10);
     }
 #ifdef IGT_PHASE_CLOCKS
-    if (clk_on) for (int i = 0; i < 16; i++) g_phase_clk[i] = clk[i];
+    if (clk_on) {
+        for (int i = 0; i < 16; i++) g_phase_clk[i] = clk[i];
+        for (int i = round_i; i < 512; i++) { g_round_clk[i] = 0; g_round_n[i] = -1; }
+    }
 #endif
 }
 #endif

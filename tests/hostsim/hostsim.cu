@@ -64,8 +64,9 @@ int hostsim_rollout(const igt_params *p, int B, int prec, const double *z0, cons
             double z[NZ], c[3] = { curv[3 * q], curv[3 * q + 1], curv[3 * q + 2] };
             for (int i = 0; i < NZ; i++) { z[i] = z0[q * NZ + i]; Z[q * (N + 1) * NZ + i] = z[i]; }
             for (int k = 0; k < N; k++) {
-                double u[2] = { U[(q * N + k) * 2], U[(q * N + k) * 2 + 1] }, zn[NZ], S[NZ][NSEED];
-                rk4_step_sens(P, z, u, c, zn, S);
+                double u[2] = { U[(q * N + k) * 2], U[(q * N + k) * 2 + 1] }, zn[NZ], Sc[NSENS], S[NZ][NSEED];
+                rk4_step_sens(P, z, u, c, zn, Sc);
+                expand_sens(P, Sc, S);
                 double zv[NZ];
                 rk4_step(P, z, u, c, zv);
                 for (int i = 0; i < NZ; i++) { if (zv[i] != zn[i]) return 1; }

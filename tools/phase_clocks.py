@@ -19,8 +19,24 @@ clk = (C.c_longlong * 16)()
 lib = _lib.load()
 lib.igt_debug_phase_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
 assert lib.igt_debug_phase_clocks(s._h, clk) == 0
-names = ["sched", "node1(sens,rows)", "adjoint+test", "node2(kkt)", "riccati", "step_bound", "sync", "rollout", "node3+collect", "idle", "accept+out"]
+names = ["sched", "node1(sens,rows)", "adjoint+test", "node2(kkt)", "riccati", "step_bound", "sync", "rollout", "collect", "idle", "accept+out", "node3"]
 tot = sum(clk)
 print("B=%d ms=%.1f total cycles %.3e (%.1f ms @1.965GHz)" % (B, e0.elapsed_time(e1), tot, tot / 1.965e6))
 for n, c in zip(names, clk):
     print("%-18s %12d  %5.1f%%" % (n, c, 100.0 * c / max(tot, 1)))
+
+if hasattr(lib, "igt_debug_round_clocks"):
+    rc, rn = (C.c_longlong * 512)(), (C.c_int * 512)()
+    lib.igt_debug_round_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    assert lib.igt_debug_round_clocks(s._h, rc, rn) == 0
+    print("round: active problems of CTA 0 / kcycles since the previous pass")
+    print(" ".join("%d:%d/%.0f" % (i, rn[i], rc[i] / 1e3) for i in range(512) if rn[i] > 0))
+
+if hasattr(lib, "igt_debug_round_phases"):
+    ph = (C.c_int * (512 * 12))()
+    lib.igt_debug_round_phases.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    assert lib.igt_debug_round_phases(s._h, ph) == 0
+    print("per pass (a pass's phases are recorded one slot late for ticks after the round marker): n | " + " ".join(n[:8] for n in names))
+    for i in range(512):
+        if rn[i] > 0 and (i < 30 or i % 4 == 0):
+            print("%3d n=%3d | " % (i, rn[i]) + " ".join("%7d" % ph[i * 12 + j] for j in range(12)))
