@@ -32,7 +32,7 @@
 #endif
 
 #ifndef IGT_PF_DIST
-#define IGT_PF_DIST 2          // stages ahead the latency-bound sweeps (adjoint, step bound) prefetch
+#define IGT_PF_DIST 1          // stages ahead the latency-bound sweeps (adjoint, step bound) prefetch
 #endif
 #ifndef IGT_PF_DIST_R
 #define IGT_PF_DIST_R 1        // ... and the Riccati sweep (compute-bound: one stage ahead is enough)
@@ -523,10 +523,8 @@ struct LogSum {
 // w = (zeta, u) (i1 < 0: single entry), 2x2 Hessian block on (x, y) (collision row only).
 // The indices travel as types so that every use indexes registers statically.  `slot` is the row's
 // fixed register slot (0,1 speed; 2,3 ey; 4 collision; 5..12 input and rate rows), the same for every
-// stage, so that a node phase can load the slacks and multipliers of all rows of a node in one burst
-// (load_rows) before it computes -- a load issued per row between the stores of the previous row
-// exposes one memory latency per row.  The terminal-set rows of stage N-1 (slot -1) are visited only
-// if CINF; the node phases run them in their own chunked loops (cinf_chunks).
+// stage.  The terminal-set rows of stage N-1 (slot -1) are visited only if CINF; the node phases run
+// them in their own loops (cinf_rows), node_phase3 both of its passes over them in one.
 template <int I> struct IC { static constexpr int value = I; };
 constexpr int NSLOT = 13;
 IGT_HD int slot_base(int N, int k) { return k == 0 ? 5 : (k == N ? 2 : 0); }      // workspace row = slot - base
@@ -569,36 +567,24 @@ IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, co
               P.cinf_A[m][1], Z0, Z0, Z0);
 }
 
-// slacks (and multipliers) of the stage rows of node k of iterate buffer b, one burst of loads into
-// slot-indexed registers; o = row_off(N, n_cinf, k)
+// prefetch the slacks (and multipliers) of all rows of node k of iterate buffer b into L1, issued before
+// the node's other work so that the per-row loads further down hit; o = row_off(N, n_cinf, k)
 template <bool WANT_S, typename T, typename W>
-IGT_HD void load_rows(const W &w, int N, int k, int b, int o, T *sv, T *yv)
+IGT_HD void prefetch_rows(const DevParams<T> &P, const W &w, int k, int b, int o)
 {
-    const int base = slot_base(N, k);
-#pragma unroll
-    for (int sl = 0; sl < NSLOT; sl++)
-        if (slot_used(N, k, sl)) {
-            yv[sl] = w.Y(b, o + sl - base);
-            if (WANT_S) sv[sl] = w.S(b, o + sl - base);
-        }
+    const int n = (k == 0 ? 8 : (k == P.N ? 3 : 13)) + (k == P.N - 1 ? P.n_cinf : 0);
+    for (int r = 0; r < n; r++) {
+        w.pf(w.L.oY[b] + o + r);
+        if (WANT_S) w.pf(w.L.oS[b] + o + r);
+    }
 }
 
-// the terminal-set rows of stage N-1 (mpc.py:177-180; workspace rows o + 13 ...) in chunks of CCH: the
-// slacks and multipliers of a chunk are loaded in one burst, then f(m, r, s, y, A0, A1, b) runs per row
-constexpr int CCH = 8;
-template <typename T, typename W, typename F>
-IGT_HD void cinf_chunks(const DevParams<T> &P, const W &w, int b, int o, F &&f)
+// the terminal-set rows of stage N-1 (mpc.py:177-180; workspace rows o + 13 ...): f(r, A0, A1, b) per row
+template <typename T, typename F>
+IGT_HD void cinf_rows(const DevParams<T> &P, int o, F &&f)
 {
 #pragma unroll 1
-    for (int m0 = 0; m0 < P.n_cinf; m0 += CCH) {
-        T s8[CCH], y8[CCH];
-#pragma unroll
-        for (int j = 0; j < CCH; j++)
-            if (m0 + j < P.n_cinf) { s8[j] = w.S(b, o + NSLOT + m0 + j); y8[j] = w.Y(b, o + NSLOT + m0 + j); }
-#pragma unroll
-        for (int j = 0; j < CCH; j++)
-            if (m0 + j < P.n_cinf) f(m0 + j, o + NSLOT + m0 + j, s8[j], y8[j], P.cinf_A[m0 + j][0], P.cinf_A[m0 + j][1], P.cinf_b[m0 + j]);
-    }
+    for (int m = 0; m < P.n_cinf; m++) f(o + NSLOT + m, P.cinf_A[m][0], P.cinf_A[m][1], P.cinf_b[m]);
 }
 
 // symmetric 11x11 / 9x9 storage (upper triangle, row-major)
@@ -726,6 +712,8 @@ template <typename T>
 IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k)
 {
     const int N = P.N, b = c.cur;
+    const int o = row_off(N, P.n_cinf, k);
+    prefetch_rows<true>(P, w, k, b, o);                          // they arrive while the sensitivities are computed
     T z[NZ], up[2], u[2];
     node_load(P, w, c, k, z, up, u);
     if (k < N) {
@@ -738,12 +726,9 @@ IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
 #pragma unroll
     for (int i = 0; i < NW; i++) gw[i] = T(0);
     T rp = T(0), s_max = T(0), sy_min = T(1e30), sy_max = T(0);
-    const int o = row_off(N, P.n_cinf, k);
-    T sv[NSLOT], yv[NSLOT];
-    load_rows<true>(w, N, k, b, o, sv, yv);
-    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto SL, int, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
-        constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-        const T s = sv[sl], y = yv[sl];
+    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
+        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        const T s = w.S(b, o + r), y = w.Y(b, o + r);
         gw[i0] += g0 * s;
         if constexpr (i1 >= 0) gw[i1] += g1 * s;
         rp = fmax(rp, fabs(cv + y));
@@ -752,7 +737,8 @@ IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
         sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
     });
     if (k == N - 1)
-        cinf_chunks(P, w, b, o, [&](int, int, T s, T y, T A0, T A1, T bb) {
+        cinf_rows(P, o, [&](int r, T A0, T A1, T bb) {
+            const T s = w.S(b, r), y = w.Y(b, r);
             const T cv = A0 * z[IV] + A1 * u[0] - bb;
             gw[IV] += A0 * s; gw[IUA] += A1 * s;
             rp = fmax(rp, fabs(cv + y));
@@ -773,6 +759,8 @@ IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
 {
     const int N = P.N, b = c.cur;
     const T mu = c.mu;
+    const int o = row_off(N, P.n_cinf, k);
+    prefetch_rows<true>(P, w, k, b, o);
     T z[NZ], up[2], u[2];
     node_load(P, w, c, k, z, up, u);
     T g[NW], H[66];
@@ -786,12 +774,9 @@ IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
         for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
         add_dyn_hessian(P, z, u, c.curv, ln, H);
     }
-    const int o = row_off(N, P.n_cinf, k);
-    T sv[NSLOT], yv[NSLOT];
-    load_rows<true>(w, N, k, b, o, sv, yv);
-    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto SL, int, T cv, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
-        constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-        const T s = sv[sl], y = yv[sl];
+    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
+        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+        const T s = w.S(b, o + r), y = w.Y(b, o + r);
         T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
         g[i0] += g0 * gr;
         H[sym11(i0, i0)] += sig * g0 * g0;
@@ -805,7 +790,8 @@ IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
         }
     });
     if (k == N - 1)
-        cinf_chunks(P, w, b, o, [&](int, int, T s, T y, T A0, T A1, T bb) {
+        cinf_rows(P, o, [&](int r, T A0, T A1, T bb) {
+            const T s = w.S(b, r), y = w.Y(b, r);
             const T cv = A0 * z[IV] + A1 * u[0] - bb;
             T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
             g[IV] += A0 * gr;
@@ -878,6 +864,8 @@ IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
 {
     const int N = P.N, b = c.cur, nb = cand_buf(c.cur, j);
     if (w.Tc(nb, 0) == T(0)) return;                            // the rollout left the finite range
+    const int o = row_off(N, P.n_cinf, k);
+    prefetch_rows<true>(P, w, k, b, o);
     T alpha = c.alpha;
     for (int i = 0; i < j; i++) alpha *= T(0.5);
     const T mu = c.mu, tau = fmax(P.tau_min, T(1) - mu);
@@ -891,13 +879,11 @@ IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
     dw[IPA] = upn[0] - up[0]; dw[IPD] = upn[1] - up[1];
     if (k < N) { dw[IUA] = w.Du(nb, k, 0); dw[IUD] = w.Du(nb, k, 1); } else { dw[IUA] = dw[IUD] = T(0); }
     const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]);
-    const int o = row_off(N, P.n_cinf, k);
     bool fail = false;
-    T sv[NSLOT], yv[NSLOT], ynv[NSLOT];
-    load_rows<true>(w, N, k, b, o, sv, yv);
+    T ynv[NSLOT];
     visit_rows<false>(P, k, z, up, u, ox, oy, [&](auto SL, int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
         constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-        const T s = sv[sl], y = yv[sl];
+        const T s = w.S(b, o + r), y = w.Y(b, o + r);
         T dc = g0 * dw[i0];
         if constexpr (i1 >= 0) dc += g1 * dw[i1];
         T yn = y - alpha * (cv + y) - dc;
@@ -918,7 +904,8 @@ IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
             lg.add(ynv[sl]);
         });
     if (k == N - 1)
-        cinf_chunks(P, w, b, o, [&](int, int r, T s, T y, T A0, T A1, T bb) {
+        cinf_rows(P, o, [&](int r, T A0, T A1, T bb) {
+            const T s = w.S(b, r), y = w.Y(b, r);
             const T cv = A0 * z[IV] + A1 * u[0] - bb;
             T dc = A0 * dw[IV];
             dc += A1 * dw[IUA];
