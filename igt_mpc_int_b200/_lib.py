@@ -38,6 +38,7 @@ class IgtParams(C.Structure):
         ("theta_mu", C.c_double), ("y_init_min", C.c_double), ("tau_min", C.c_double),
         ("mu0_warm", C.c_double), ("y_init_min_warm", C.c_double),
         ("reg_min", C.c_double), ("reg_up", C.c_double), ("reg_down", C.c_double), ("reg_max", C.c_double),
+        ("reg_jump", C.c_double),
         ("eps_phi", C.c_double), ("gamma_theta", C.c_double), ("theta_small", C.c_double),
         ("max_iter", C.c_int), ("n_alpha", C.c_int), ("second_order", C.c_int),
         ("stall_iter", C.c_int), ("stall_rp", C.c_double), ("max_trials", C.c_int), ("precision", C.c_int),

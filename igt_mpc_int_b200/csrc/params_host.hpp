@@ -24,6 +24,7 @@ inline void fill_dev_params(const igt_params &p, DevParams<T> &d)
     d.theta_mu = T(p.theta_mu); d.y_init_min = T(p.y_init_min); d.tau_min = T(p.tau_min);
     d.mu0_warm = T(p.mu0_warm); d.y_init_min_warm = T(p.y_init_min_warm); d.alpha_safety = T(0.99);
     d.reg_min = T(p.reg_min); d.reg_up = T(p.reg_up); d.reg_down = T(p.reg_down); d.reg_max = T(p.reg_max);
+    d.reg_jump = T(p.reg_jump);
     d.eps_phi = T(p.eps_phi); d.gamma_theta = T(p.gamma_theta); d.theta_small = T(p.theta_small);
     for (int m = 0; m < p.n_cinf; m++) {
         d.cinf_A[m][0] = T(p.cinf_A[m][0]); d.cinf_A[m][1] = T(p.cinf_A[m][1]); d.cinf_b[m] = T(p.cinf_b[m]);
@@ -40,7 +41,7 @@ inline int default_params(igt_params *p, int precision)
     p->da_max = 0.1 * 0.9; p->ddf_max = 0.1 * 0.7; p->d_min = 5.6; p->w_u = 0.05;
     p->n_cinf = 0;
     p->mu0 = 0.3; p->kappa_eps = 10.0; p->kappa_mu = 0.2; p->theta_mu = 1.5; p->y_init_min = 0.3;
-    p->tau_min = 0.99; p->reg_min = 1e-4; p->reg_up = 10.0; p->reg_down = 10.0; p->reg_max = 1e10;
+    p->tau_min = 0.99; p->reg_min = 1e-4; p->reg_up = 10.0; p->reg_down = 10.0; p->reg_max = 1e10; p->reg_jump = 1.1;
     p->gamma_theta = 1e-6; p->max_iter = 60; p->n_alpha = 6; p->second_order = 1;
     p->mu0_warm = 1e-4; p->y_init_min_warm = 1e-3;
     p->stall_iter = 16; p->stall_rp = 1e-2; p->max_trials = 0;

@@ -65,7 +65,7 @@ struct DevParams {
     T dt, h, l_r, lsum, inv_lr, rho;
     T v_min, v_max, a_min, a_max, df_max, ey_lim, da_max, ddf_max, d_min, w_u;
     T tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min, mu0_warm, y_init_min_warm, alpha_safety, stall_rp;
-    T reg_min, reg_up, reg_down, reg_max, eps_phi, gamma_theta, theta_small;
+    T reg_min, reg_up, reg_down, reg_max, reg_jump, eps_phi, gamma_theta, theta_small;
     T cinf_A[MAX_CINF][2], cinf_b[MAX_CINF];
     T Wn[36], mu_f[6], sigma_t, mu_t;
     const T *W[MAX_MLP_LAYERS], *b[MAX_MLP_LAYERS];   // device pointers, row-major [out][in]
@@ -935,6 +935,7 @@ struct Solver {
     int status, iters, ls, need_back, trials;   // need_back: 2 = full backward, 1 = Riccati only, 0 = none
     bool done;
     T mu, reg, alpha, Jcur, lgcur, thetacur, phi;
+    T reg_hint;               // set by a failed Riccati sweep: the shift that makes the failing stage's Quu positive definite
     T stat, rp, s_max, sy_min, sy_max;
     TermVal<T> tcur, tcand;
     T Jcand, lgcand, thetacand;   // trial quantities (without the terminal value term)
@@ -1105,7 +1106,7 @@ struct Solver {
         const int N = P.N;
         load_inputs(io, p, has_ctx);
         cur = 0; status = 1; iters = 0; ls = 0; need_back = 2; done = false; trials = 0;
-        mu = warm ? P.mu0_warm : P.mu0; reg = T(0); alpha = T(1);
+        mu = warm ? P.mu0_warm : P.mu0; reg = T(0); alpha = T(1); reg_hint = T(0);
         const T y_min = warm ? P.y_init_min_warm : P.y_init_min;
         {   // rows on x0 alone: mpc.py:316-317 and :298-299 at k = 0
             T tol = T(1e-9);
@@ -1291,7 +1292,12 @@ struct Solver {
             for (int e = 0; e < NHE; e++) H[sym11(he_i(e), he_j(e))] += w.Hl(k, e);
             T q00 = H[sym11(IUA, IUA)] + reg, q11 = H[sym11(IUD, IUD)] + reg, q01 = H[sym11(IUA, IUD)];
             T det = q00 * q11 - q01 * q01;
-            if (!(q00 > T(0) && det > T(1e-12) * q00 * q11)) return false;
+            if (!(q00 > T(0) && det > T(1e-12) * q00 * q11)) {
+                const T a_ = H[sym11(IUA, IUA)], b_ = H[sym11(IUD, IUD)];
+                const T lmin = T(0.5) * (a_ + b_) - sqrt(T(0.25) * (a_ - b_) * (a_ - b_) + q01 * q01);
+                reg_hint = lmin < T(0) ? -lmin * P.reg_jump : T(0);
+                return false;
+            }
             T idet = T(1) / det;
             T i00 = q11 * idet, i11 = q00 * idet, i01 = -q01 * idet;
             T k0 = -(i00 * g[IUA] + i01 * g[IUD]), k1 = -(i01 * g[IUA] + i11 * g[IUD]);
@@ -1332,7 +1338,14 @@ struct Solver {
         for (int k = 0; k <= N; k++) {
             T z[NZ], up[2], u[2] = { T(0), T(0) }, dw[NW];
             prefetch_bound(b, k + IGT_PF_DIST);
+            // every load of the stage is issued up front (one exposed memory latency per stage, not one per row:
+            // the rows below branch, so the compiler cannot hoist their loads itself)
+            const int o = row_off(N, P.n_cinf, k), sb0 = slot_base(N, k);
+            T yv[NSLOT], F[NA][NW];
+#pragma unroll
+            for (int sl = 0; sl < NSLOT; sl++) if (slot_used(N, k, sl)) yv[sl] = w.Y(b, o + sl - sb0);
             load_z(b, k, z); load_up(b, k, up);
+            if (k < N) load_F(P, w, k, F);
 #pragma unroll
             for (int i = 0; i < NA; i++) dw[i] = dz[i];
             dw[IUA] = T(0); dw[IUD] = T(0);
@@ -1343,18 +1356,33 @@ struct Solver {
                 for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dz[j]; d1 += w.KK(k, 1, j) * dz[j]; }
                 dw[IUA] = d0; dw[IUD] = d1;
             }
-            int o = row_off(N, P.n_cinf, k);
-            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](auto, int r, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
-                constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
-                T y = w.Y(b, o + r);
+            visit_rows<false>(P, k, z, up, u, ox(k), oy(k), [&](auto SL, int, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
+                constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+                const T y = yv[sl];
                 T dc = g0 * dw[i0];
                 if constexpr (i1 >= 0) dc += g1 * dw[i1];
                 T dy = -(c + y) - dc;
                 if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
             });
+            if (k == N - 1) {
+#pragma unroll 1
+                for (int m0 = 0; m0 < P.n_cinf; m0 += 8) {
+                    T y8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (m0 + j < P.n_cinf) y8[j] = w.Y(b, o + NSLOT + m0 + j);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (m0 + j < P.n_cinf) {
+                            const T A0 = P.cinf_A[m0 + j][0], A1 = P.cinf_A[m0 + j][1], y = y8[j];
+                            const T c = A0 * z[IV] + A1 * u[0] - P.cinf_b[m0 + j];
+                            T dc = A0 * dw[IV];
+                            dc += A1 * dw[IUA];
+                            T dy = -(c + y) - dc;
+                            if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
+                        }
+                }
+            }
             if (k == N) break;
-            T F[NA][NW];
-            load_F(P, w, k, F);
 #pragma unroll
             for (int i = 0; i < NA; i++) {
                 T acc = T(0);
@@ -1384,7 +1412,7 @@ struct Solver {
     {
         for (;;) {
             if (riccati_sweep()) break;
-            reg = fmax(reg * P.reg_up, P.reg_min);
+            reg = fmax(fmax(reg * P.reg_up, P.reg_min), reg_hint);
             if (reg > P.reg_max) { status = 3; done = true; return; }
         }
         need_back = 0;
@@ -1826,7 +1854,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
 #ifdef IGT_PHASE_CLOCKS
             for (;;) {
                 if (sv.riccati_sweep()) break;
-                sv.reg = fmax(sv.reg * P.reg_up, P.reg_min);
+                sv.reg = fmax(fmax(sv.reg * P.reg_up, P.reg_min), sv.reg_hint);
                 if (sv.reg > P.reg_max) { sv.status = 3; sv.done = true; break; }
             }
             IGT_TICK(4);

@@ -64,6 +64,8 @@ typedef struct {
     double mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min;
     double mu0_warm, y_init_min_warm;   /* used instead of mu0 / y_init_min when u_init is given */
     double reg_min, reg_up, reg_down, reg_max;
+    double reg_jump;   /* after a Riccati stage whose Quu + reg I is not positive definite: reg >= reg_jump * (-lambda_min(Quu))
+                          of that stage (besides reg * reg_up), so the inertia correction takes 1-2 retries, not 6 */
     double eps_phi, gamma_theta, theta_small;
     int max_iter;      /* mpc.py:137 uses 100*N for IPOPT */
     int n_alpha;       /* step halvings per line search (1..6: one iterate buffer per halving) */

@@ -31,6 +31,7 @@ class CParams(C.Structure):
         ("max_iter", C.c_int), ("n_alpha", C.c_int), ("second_order", C.c_int),
         ("max_ls_fail", C.c_int), ("max_trials", C.c_int), ("predict_alpha", C.c_int),
         ("alpha_safety", C.c_double),
+        ("reg_jump", C.c_double),
         ("stall_iter", C.c_int), ("stall_rp", C.c_double),
         ("n_layers", C.c_int), ("dims", C.c_int * (MAX_LAYERS + 1)),
         ("W", _dp * MAX_LAYERS), ("b", _dp * MAX_LAYERS),

@@ -46,6 +46,7 @@ typedef struct {
     int max_iter, n_alpha, second_order;
     int max_ls_fail, max_trials, predict_alpha;
     double alpha_safety;
+    double reg_jump;                   /* after a non-PD Quu: reg >= reg_jump * (-lambda_min(Quu)) of that stage */
     int stall_iter; double stall_rp;   /* local-infeasibility exit: it >= stall_iter and |c + y|_inf > stall_rp -> status 5 */   /* give up after this many consecutive failed line searches / total forward passes */
     /* gt_mpc value term (mpc.py:326-354,:367-369; model.py:14-67); n_layers = 0 -> 'mpc' mode */
     int n_layers;
@@ -608,6 +609,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
         /* sweep 3: Riccati */
         int ok;
         for (;;) {
+            double reg_hint = 0.0;
             ok = 1;
             double Vx[NA], Vxx[NA][NA];
             {
@@ -691,7 +693,14 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                 /* solve for the control */
                 double q00 = H[IUA][IUA] + reg, q11 = H[IUD][IUD] + reg, q01 = H[IUA][IUD];
                 double det = q00 * q11 - q01 * q01;
-                if (!(q00 > 0 && det > 1e-12 * q00 * q11)) { ok = 0; break; }
+                if (!(q00 > 0 && det > 1e-12 * q00 * q11)) {
+                    /* the shift that makes this stage's Quu positive definite */
+                    double a_ = H[IUA][IUA], b_ = H[IUD][IUD];
+                    double lmin = 0.5 * (a_ + b_) - sqrt(0.25 * (a_ - b_) * (a_ - b_) + q01 * q01);
+                    reg_hint = lmin < 0 ? -lmin * P->reg_jump : 0.0;
+                    ok = 0;
+                    break;
+                }
                 double i00 = q11 / det, i11 = q00 / det, i01 = -q01 / det;
                 double *ku = w->ku + 2 * k, *Ku = w->Ku + 2 * NA * k;
                 ku[0] = -(i00 * g[IUA] + i01 * g[IUD]);
@@ -722,7 +731,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                 }
             }
             if (ok) break;
-            reg = fmax(reg * P->reg_up, P->reg_min);
+            reg = fmax(fmax(reg * P->reg_up, P->reg_min), reg_hint);
             if (reg > P->reg_max) break;
         }
         if (reg > P->reg_max) { status = 3; break; }
@@ -851,6 +860,7 @@ void igt_oracle_default_options(igt_oracle_params *P)
     P->eps_phi = 1e-12; P->gamma_theta = 1e-6; P->theta_small = 1e-10;
     P->max_iter = 300; P->n_alpha = 6; P->second_order = 1;
     P->max_ls_fail = 1000; P->max_trials = 1000000; P->predict_alpha = 1; P->alpha_safety = 0.99;
+    P->reg_jump = 1.1;
     P->stall_iter = 16; P->stall_rp = 1e-2;
 }
 

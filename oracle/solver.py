@@ -41,6 +41,7 @@ class Options:
     reg_up = 10.0
     reg_down = 10.0
     reg_max = 1e10
+    reg_jump = 1.1       # after a non-positive-definite Quu: reg >= reg_jump * (-lambda_min(Quu)) of that stage
     n_alpha = 6
     eps_phi = 1e-12
     gamma_theta = 1e-6
@@ -306,6 +307,7 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
         # ---- sweep 3 (backward): Riccati on the perturbed KKT system --------------------
         while True:
             ok = True
+            reg_hint = 0.0
             c, Cx, Cu, hxy = rows[N]
             s, y = S[N], Y[N]
             rhat = s * c + mu
@@ -345,6 +347,11 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
                 det = Qr[0, 0] * Qr[1, 1] - Qr[0, 1] * Qr[1, 0]
                 if not (Qr[0, 0] > 0 and det > 1e-12 * Qr[0, 0] * Qr[1, 1]):
                     ok = False
+                    # the shift that makes this stage's Quu positive definite (inertia-correction shortcut
+                    # instead of climbing reg_up by reg_up)
+                    a_, b_, c_ = Quuh[0, 0], Quuh[1, 1], Quuh[0, 1]
+                    lmin = 0.5 * (a_ + b_) - np.sqrt(0.25 * (a_ - b_) ** 2 + c_ * c_)
+                    reg_hint = -lmin * opt.reg_jump if lmin < 0 else 0.0
                     break
                 Qinv = np.array([[Qr[1, 1], -Qr[0, 1]], [-Qr[1, 0], Qr[0, 0]]]) / det
                 ku[k] = -Qinv @ Quh
@@ -358,7 +365,7 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
                 Vxx = 0.5 * (Vxx + Vxx.T)
             if ok:
                 break
-            reg = max(reg * opt.reg_up, opt.reg_min)
+            reg = max(reg * opt.reg_up, opt.reg_min, reg_hint)
             if reg > opt.reg_max:
                 break
         if reg > opt.reg_max:
