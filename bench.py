@@ -44,6 +44,7 @@ WORKLOADS = {
     "cfg3_gt_mpc_16384": ("mid_episode", 16384, 40, "gt_mpc"),
 }
 DEFAULT_WORKLOAD = "cfg2_mpc_sc1-8_4096ic"
+MAX_ITER_DEFAULT = 40        # the library's default iteration cap (igt_default_params); the CPU arm uses the same
 
 
 def make_problems(name, rank):
@@ -126,10 +127,10 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     n_sample = min(len(x0), max(256, 64 * cores))
     for _ in range(args.warmup):
-        cpu_baseline(x0, up, cv, ob, N, mode, mlp, min(256, n_sample), 60)
+        cpu_baseline(x0, up, cv, ob, N, mode, mlp, min(256, n_sample), MAX_ITER_DEFAULT)
     conv, tsum = 0, 0.0
     for _ in range(args.steps):
-        c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, 60)
+        c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, MAX_ITER_DEFAULT)
         conv += c
         tsum += dt
     val = conv / tsum

@@ -32,9 +32,8 @@ using namespace igt;
 __constant__ DevParams<float> c_Pf;
 __constant__ DevParams<double> c_Pd;
 
-template <typename T> struct ConstP;
-template <> struct ConstP<float> { static __device__ __forceinline__ const DevParams<float> &get() { return c_Pf; } };
-template <> struct ConstP<double> { static __device__ __forceinline__ const DevParams<double> &get() { return c_Pd; } };
+template <> struct igt::ConstP<float> { static __device__ __forceinline__ const DevParams<float> &get() { return c_Pf; } };
+template <> struct igt::ConstP<double> { static __device__ __forceinline__ const DevParams<double> &get() { return c_Pd; } };
 
 // ------------------------------------------------------------------ kernels -------------
 // cold-start guess: best of five tracking-controller rollouts per problem -> guess[B][N][2]

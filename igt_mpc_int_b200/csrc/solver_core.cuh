@@ -1663,21 +1663,45 @@ __device__ __forceinline__ int cta_list_build(bool need, long bound, const Solve
     return n;
 }
 
+// The item loops of the CTA-wide phases live in functions of their own (not inlined): each gets its own
+// register allocation, so that the spills of one phase do not leak into the others or into the
+// per-problem sweeps of the main loop.  The parameters come from constant memory through ConstP<T>,
+// which the translation unit defines.
+template <typename T> struct ConstP;
+
+template <typename T, int PHASE>
+__device__ __noinline__ void phase_items(T *ws_base, const NodeList<T> *nl, int n, int n_spec)
+{
+    const DevParams<T> &P = ConstP<T>::get();
+    Ws<T> w; w.L.init(P.N, P.n_cinf);
+    if (PHASE == 1 || PHASE == 2) {
+        const int total = n * (P.N + 1);
+        for (int it = threadIdx.x; it < total; it += blockDim.x) {
+            const int j = it % n, k = it / n;
+            w.bind(ws_base, nl->slot[j]);
+            if (PHASE == 1) node_phase1(P, w, nl->ctx[j], k);
+            else node_phase2(P, w, nl->ctx[j], k);
+        }
+    } else if (PHASE == 3) {                                      // rollouts of the line-search candidates
+        for (int it = threadIdx.x; it < n * n_spec; it += blockDim.x) {
+            const int q = it % n, j = it / n;
+            if (j < P.n_alpha - nl->ctx[q].ls) { w.bind(ws_base, nl->slot[q]); rollout_item(P, w, nl->ctx[q], j); }
+        }
+    } else {                                                      // rows of the trial points
+        const int total = n * n_spec * (P.N + 1);
+        for (int it = threadIdx.x; it < total; it += blockDim.x) {
+            const int q = it % n, r = it / n, j = r % n_spec, k = r / n_spec;
+            if (j < P.n_alpha - nl->ctx[q].ls) { w.bind(ws_base, nl->slot[q]); node_phase3(P, w, nl->ctx[q], k, j); }
+        }
+    }
+}
+
 template <typename T, int PHASE>
 __device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
                                                long bound, const Solver<T> &sv, NodeList<T> &nl)
 {
     const int n = cta_list_build(need, bound, sv, nl);
-    if (n > 0) {
-        Ws<T> w; w.L = L;
-        const int total = n * (P.N + 1);
-        for (int it = threadIdx.x; it < total; it += blockDim.x) {
-            const int j = it % n, k = it / n;
-            w.bind(ws_base, nl.slot[j]);
-            if (PHASE == 1) node_phase1(P, w, nl.ctx[j], k);
-            else node_phase2(P, w, nl.ctx[j], k);
-        }
-    }
+    if (n > 0) phase_items<T, PHASE>(ws_base, &nl, n, 1);
     __syncthreads();
 }
 
@@ -1702,18 +1726,10 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
     if (n == 0) { IGT_MID_TICK(); return 1; }                     // CTA-uniform
     int n_spec = 1;
     if (speculate) { n_spec = (int)blockDim.x / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
-    Ws<T> w; w.L = L;
-    for (int it = threadIdx.x; it < n * n_spec; it += blockDim.x) {
-        const int q = it % n, j = it / n;
-        if (j < P.n_alpha - nl.ctx[q].ls) { w.bind(ws_base, nl.slot[q]); rollout_item(P, w, nl.ctx[q], j); }
-    }
+    phase_items<T, 3>(ws_base, &nl, n, n_spec);
     __syncthreads();
     IGT_MID_TICK();
-    const int total = n * n_spec * (P.N + 1);
-    for (int it = threadIdx.x; it < total; it += blockDim.x) {
-        const int q = it % n, r = it / n, j = r % n_spec, k = r / n_spec;
-        if (j < P.n_alpha - nl.ctx[q].ls) { w.bind(ws_base, nl.slot[q]); node_phase3(P, w, nl.ctx[q], k, j); }
-    }
+    phase_items<T, 4>(ws_base, &nl, n, n_spec);
     __syncthreads();
     return n_spec;
 }

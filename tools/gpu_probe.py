@@ -22,6 +22,7 @@ def main():
     for prec in precs:
         kw = {}
         if os.environ.get('IGT_MAX_TRIALS'): kw['max_trials'] = int(os.environ['IGT_MAX_TRIALS'])
+        if os.environ.get('IGT_MAX_ITER'): kw['max_iter'] = int(os.environ['IGT_MAX_ITER'])
         s = BatchSolver(N=N, precision=prec, **kw)
         out = s.solve_batch_device(x0, up, cv, ob); torch.cuda.synchronize()
         for _ in range(reps):
