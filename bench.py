@@ -44,7 +44,7 @@ WORKLOADS = {
     "cfg3_gt_mpc_16384": ("mid_episode", 16384, 40, "gt_mpc"),
 }
 DEFAULT_WORKLOAD = "cfg2_mpc_sc1-8_4096ic"
-MAX_ITER_DEFAULT = 40        # the library's default iteration cap (igt_default_params); the CPU arm uses the same
+MAX_ITER_DEFAULT = 60        # the library's default iteration cap (igt_default_params); the CPU arm uses the same
 
 
 def make_problems(name, rank):
@@ -287,11 +287,12 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        traffic = None                                        # dram bytes per launch from the committed ncu capture
+        traffic = traffic_gbs = None                          # dram bytes per launch from the committed ncu capture
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if tr.get("workload") == args.workload and tr.get("precision") == args.precision:
                 traffic = tr["dram_bytes_per_launch"]
+                traffic_gbs = traffic / (tr["launch_ms_under_ncu"] * 1e-3) / 1e9
         except Exception:
             pass
         kernel_ms = dev_ms / args.steps                       # solver + guess kernels of one step on this rank
@@ -315,8 +316,11 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
-                         "note": "algorithmic bytes 8*(11N+24) per solve; the solver is CUDA-core/latency bound, "
-                                 "see compute_roofline (SURVEY 8(d))"},
+                         "traffic_gbs": traffic_gbs, "traffic_frac": None if traffic_gbs is None else traffic_gbs / hbm_peak,
+                         "note": "achieved = algorithmic bytes 8*(11N+24) per solve / kernel time; traffic = DRAM bytes of "
+                                 "the solver kernel in the committed ncu capture (its per-problem workspace streams "
+                                 "through HBM in every phase of every iteration: traffic_gbs / peak is the bandwidth "
+                                 "actually drawn), see also compute_roofline (SURVEY 8(d))"},
             "compute_roofline": {"bound": "%s-fma" % args.precision, "achieved": alg_flops / (kernel_ms * 1e-3) / 1e12,
                                  "peak": fma_peak, "unit": "TFLOP/s",
                                  "frac": alg_flops / (kernel_ms * 1e-3) / 1e12 / fma_peak,

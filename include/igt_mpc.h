@@ -67,9 +67,10 @@ typedef struct {
     double reg_jump;   /* after a Riccati stage whose Quu + reg I is not positive definite: reg >= reg_jump * (-lambda_min(Quu))
                           of that stage (besides reg * reg_up), so the inertia correction takes 1-2 retries, not 6 */
     double eps_phi, gamma_theta, theta_small;
-    int max_iter;      /* iteration cap -> IGT_STATUS_MAXITER (mpc.py:137 gives IPOPT 100*N; default here 40: 98.8 % of the
-                          problems that converge within 60 iterations do so within 40, and the stragglers beyond that cost
-                          a sixth of a batch's run time -- DESIGN.md section 4) */
+    int max_iter;      /* iteration cap -> IGT_STATUS_MAXITER (mpc.py:137 gives IPOPT 100*N).  Default 60.  A batch is one
+                          wave of problems, so its run time follows its slowest problem: a cap of 40 keeps 98.8 % of the
+                          converged solves and is 18 % faster, but costs closed-loop episodes extra brake fallbacks
+                           */
     int n_alpha;       /* step halvings per line search (1..6: one iterate buffer per halving) */
     int second_order;  /* add the dt*Hess(lambda.f) curvature term to the Riccati pass */
     int stall_iter;    /* local-infeasibility exit: iteration >= stall_iter and ... */

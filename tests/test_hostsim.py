@@ -80,11 +80,11 @@ def test_core_x0_infeasible_and_warm_start(oracle_params, cinf):
 
 
 def test_core_iteration_and_trial_budgets_match_oracle(oracle_params, cinf):
-    """max_iter 40 (default) and a budget of 150 forward passes against the oracle run with the
+    """max_iter 60 (default) and a budget of 150 forward passes against the oracle run with the
     same budgets: the same problems are given up on, with the same status."""
     pb = S.mid_episode(256, N=40, seed=2026)
     p = H.default_params(1); p.set_cinf(*cinf)
-    assert p.max_iter == 40 and p.max_trials == 0
+    assert p.max_iter == 60 and p.max_trials == 0
     p.max_trials = 150
     r = H.solve(p, pb.x0, pb.u_prev, pb.curv, pb.obs)
     o = c_oracle.COracle(oracle_params[40], max_iter=p.max_iter, max_trials=p.max_trials).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
