@@ -1,7 +1,8 @@
 """Batched closed-loop episode driver: E independent two-vehicle episodes advance
 together, one batched MPC solve per 0.1 s step for all 2E vehicles.
 
-Mirrors the per-timestep glue of the reference's `evaluate.py` 'mpc' branch (evaluate.py:451-564):
+Mirrors the per-timestep glue of the reference's `evaluate.py`, 'mpc' branch (evaluate.py:451-564) and
+'gt_mpc' branch (evaluate.py:198-312; differences listed at `run_closed_loop`):
   predict            constant-acceleration forecast      common/constant_acceleration_model.py:18-82
   share forecasts    a vehicle that solved at t-1 is forecast by its own plan   common/utils.py:339-352
   filter_preds       obstacles behind the ego -> (-20, -20)                     common/utils.py:365-388
@@ -73,7 +74,14 @@ def _ca_step(s, v, a, dt):
     return s + v * dt + 0.5 * a * dt * dt, min(max(v + a * dt, V_PRED_MIN), V_PRED_MAX)
 
 
-def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_latency=False):
+def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_latency=False, mode="mpc"):
+    """mode 'gt_mpc' (the solver must have been given the value network): previous input (0, 0) instead of
+    (0.1, 0) (evaluate.py:171 / :419); the first forecast assumes a = 0.09 (i + 1) for vehicle i
+    (evaluate.py:207-210); warm starts only from t = 2 on (evaluate.py:232-235); every solve gets
+    nn_ctx = (s_tv, v_tv, e_tv, e_ego): the other vehicle's forecast at step N (mpc.py:330) and the
+    scenario codes of utils.scenario_encoding (mpc.py:336-337)."""
+    assert mode in ("mpc", "gt_mpc")
+    gt = mode == "gt_mpc"
     E = len(specs)
     B = 2 * E
     routes = [sp.routes for sp in specs]
@@ -85,7 +93,8 @@ def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_la
             if sp.routes[i] in ('32', '41'):
                 th = abs(th)                                                               # mpc.py:282-283
             z[2 * e + i] = (x, y, sp.s0[i], 0.0, 0.0, 0.0, th)                             # evaluate.py:404-418, v0 = 0
-    u_prev = np.tile([0.1, 0.0], (B, 1))                                                   # evaluate.py:419
+    u_prev = np.tile([0.0, 0.0] if gt else [0.1, 0.0], (B, 1))                             # evaluate.py:171 / :419
+    enc = np.array([G.scenario_encoding(sp.routes) for sp in specs], dtype=np.float64).reshape(B)   # e of every vehicle
     z_cl = np.zeros((E, 2, steps + 1, 7)); u_cl = np.zeros((E, 2, steps, 2))
     solved = np.zeros((E, 2, steps), dtype=bool)
     z_cl[:, :, 0] = z.reshape(E, 2, 7)
@@ -107,6 +116,8 @@ def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_la
                 fc[b, N] = (*_route_xy(s1, route), s1, v1)
             else:
                 s, v, a = z[b, 2], z[b, 5], u_prev[b, 0]
+                if gt and t == 0:
+                    a = 0.09 * (b % 2 + 1)                                                 # evaluate.py:207-210
                 fc[b, 0] = (z[b, 0], z[b, 1], s, v)
                 for k in range(N):
                     s, v = _ca_step(s, v, a, dt)
@@ -120,11 +131,17 @@ def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_la
         t0 = time.perf_counter()
         u_init = np.concatenate([prev_u[:, 1:], prev_u[:, -1:]], axis=1)                   # utils.py:362
         out = dict(x=np.zeros((B, N + 1, 7)), u=np.zeros((B, N, 2)), status=np.ones(B, dtype=np.int32))
-        for mask, warm in ((prev_ok, True), (~prev_ok, False)):
+        nn_ctx = None
+        if gt:
+            other = np.arange(B) ^ 1
+            nn_ctx = np.stack([fc[other, N, 2], fc[other, N, 3], enc[other], enc], axis=1)  # mpc.py:326-337
+        warm_ok = prev_ok & (t > 1) if gt else prev_ok                                     # evaluate.py:232-235 / :478-481
+        for mask, warm in ((warm_ok, True), (~warm_ok, False)):
             idx = np.where(mask)[0]
             if len(idx) == 0:
                 continue
-            r = solver.solve_batch(z[idx], u_prev[idx], curv[idx], obs[idx], u_init=u_init[idx] if warm else None)
+            kw = dict(nn_ctx=nn_ctx[idx]) if gt else {}
+            r = solver.solve_batch(z[idx], u_prev[idx], curv[idx], obs[idx], u_init=u_init[idx] if warm else None, **kw)
             out["x"][idx], out["u"][idx], out["status"][idx] = r["x"], r["u"], r["status"]
         if record_latency:
             lat.append(1e3 * (time.perf_counter() - t0))

@@ -6,17 +6,18 @@ from oracle import nlp, c_oracle
 
 
 class OracleBackend:
-    def __init__(self, N=40, **options):
+    def __init__(self, N=40, mlp=None, **options):
         self.N = N
         self.P = nlp.Params(N=N)
         self.options = options
-        self.cold = c_oracle.COracle(self.P, **options)
+        term = None if mlp is None else nlp.MLPTerm(**mlp)
+        self.cold = c_oracle.COracle(self.P, term, **options)
         warm = dict(options); warm.update(mu0=1e-4, y_init_min=1e-3)      # igt_params mu0_warm / y_init_min_warm
-        self.warm = c_oracle.COracle(self.P, **warm)
+        self.warm = c_oracle.COracle(self.P, term, **warm)
 
     def solve_batch(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None):
         co = self.warm if u_init is not None else self.cold
-        r = co.solve(x0, u_prev, curv, obs_xy, u_init=u_init)
+        r = co.solve(x0, u_prev, curv, obs_xy, nn_ctx=nn_ctx, u_init=u_init)
         return dict(x=r["Z"], u=r["U"], cost=r["cost"], viol=r["viol"], status=r["status"], iters=r["iters"])
 
     def evaluate(self, x0, u_prev, curv, obs_xy, u, nn_ctx=None):

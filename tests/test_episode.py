@@ -55,3 +55,57 @@ def test_closed_loop_outcomes_match_oracle_all_scenarios():
     same = rg.solved == ro.solved
     assert same.mean() > 0.99
     gpu.close()
+
+
+def _value_net(hidden=(128, 128), seed=2026):
+    import torch
+    torch.manual_seed(seed)
+    dims = [6] + list(hidden) + [1]
+    layers = [torch.nn.Linear(dims[i], dims[i + 1], dtype=torch.double) for i in range(len(dims) - 1)]
+    w = [(l.weight.detach().numpy().copy(), l.bias.detach().numpy().copy()) for l in layers]
+    return dict(weights=w, Wn=np.eye(6), mu_f=np.zeros(6), sigma_t=1.0, mu_t=0.0)
+
+
+def test_closed_loop_gt_mpc_host_logic_with_oracle_backend():
+    """'gt_mpc' branch of the loop (evaluate.py:198-312): previous input (0, 0), first forecast with
+    a = 0.09 (i + 1), value-network context per vehicle, warm starts from t = 2 on."""
+    calls = []
+
+    class Spy(OracleBackend):
+        def solve_batch(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None):
+            calls.append((np.array(u_prev), None if nn_ctx is None else np.array(nn_ctx), u_init is not None))
+            return super().solve_batch(x0, u_prev, curv, obs_xy, nn_ctx=nn_ctx, u_init=u_init)
+
+    specs = episode.reference_episode_specs(scenarios=[2])[:2]
+    res = episode.run_closed_loop(Spy(N=10, mlp=_value_net((16,)), max_iter=60), specs, steps=4, N=10, mode="gt_mpc")
+    assert res.z_cl.shape == (2, 2, 5, 7)
+    up0, ctx0, warm0 = calls[0]
+    assert np.all(up0 == 0.0) and not warm0 and ctx0.shape == (4, 4)
+    enc = G.scenario_encoding(specs[0].routes)
+    assert list(ctx0[0, 2:]) == [enc[1], enc[0]] and list(ctx0[1, 2:]) == [enc[0], enc[1]]      # (e_tv, e_ego)
+    # the other vehicle's constant-acceleration forecast at step N with a = 0.09 (i + 1): s_N = s0 + a (N dt)^2 / 2
+    assert abs(ctx0[0, 0] - (specs[0].s0[1] + 0.5 * 0.18 * 1.0)) < 1e-9 and abs(ctx0[0, 1] - 0.18) < 1e-12
+    assert not calls[1][2]                                       # t = 1 is still a cold start (evaluate.py:232-235)
+    assert any(c[2] for c in calls[2:])                          # warm starts from t = 2 on
+
+
+@pytest.mark.gpu
+def test_closed_loop_gt_mpc_outcomes_match_oracle():
+    """gt_mpc closed loop, random-init value network, scenarios 1-8 variant 0: the fp64
+    CUDA-core value term against the oracle, and the tensor-core value term through its outcome flags."""
+    from igt_mpc_int_b200.planner import BatchSolver
+    net = _value_net()
+    specs = episode.reference_episode_specs()[::8]
+    ro = episode.run_closed_loop(OracleBackend(N=40, mlp=net, max_iter=60), specs, steps=150, N=40, mode="gt_mpc")
+    for tc in (0, 1):
+        gpu = BatchSolver(N=40, mlp=net)
+        gpu.set_option("tensor_core_mlp", tc)
+        rg = episode.run_closed_loop(gpu, specs, steps=150, N=40, mode="gt_mpc")
+        gpu.close()
+        assert not rg.collision.any()
+        assert np.array_equal(rg.collision, ro.collision)
+        assert np.mean(rg.deadlock == ro.deadlock) >= (1.0 if tc == 0 else 0.75)
+        assert np.mean(rg.goal == ro.goal) >= (1.0 if tc == 0 else 0.75)
+        if tc == 0:
+            dz = np.abs(rg.z_cl - ro.z_cl).reshape(len(specs), -1).max(axis=1)
+            assert np.mean(dz < 1e-3) >= 0.75, dz

@@ -66,3 +66,18 @@ def test_pcg_stream_known_answer():
     r = np.random.default_rng(2026)
     ref = [0.17893481367543618, 0.6399131657151546, 0.4672684011434851, 0.37050052710804804]
     assert np.allclose([r.random() for _ in range(4)], ref, rtol=0, atol=0)
+
+
+def test_reference_track_generator_matches_reference_output(golden):
+    """igt_mpc_int_b200.reference_track restates common/ReferenceGen.py:41-235; the golden tracks were written
+    by the reference's own ReferenceGenerator (tests/golden/make_golden.py) -- sample for sample, bit for bit."""
+    from igt_mpc_int_b200 import reference_track as RT
+    g = golden["geometry"]
+    for i, route in enumerate(str(r) for r in g["routes"]):
+        x0, y0, _ = G.start_pose(route[0])
+        t = RT.crop_track(RT.generate_track(route), x0, y0, 150)
+        assert t.shape == (6, 151)
+        assert np.array_equal(t, g["tracks"][i]), route
+    # a vehicle that starts further down the road gets the track from its nearest sample on
+    d = RT.reference_dict('12', 7.3, 2.8)
+    assert abs(d['x'][0] - 7.5) < 1e-12 and d['K'][0] == 0.0 and len(d['s']) == 151
