@@ -121,6 +121,7 @@ class COracle:
     def eval(self, x0, u_prev, curv, obs, Z, U, nn_ctx=None):
         x0, u_prev, curv, obs, Z, U, nn_ctx = map(_c, (x0, u_prev, curv, obs, Z, U, nn_ctx))
         B = x0.shape[0]
+        assert self.cp.n_layers == 0 or nn_ctx is not None, "this oracle has a value network: eval needs nn_ctx"
         cost, viol = np.empty(B), np.empty(B)
         self.lib.igt_oracle_eval(C.byref(self.cp), B, _ptr(x0), _ptr(u_prev), _ptr(curv), _ptr(obs),
                                  _ptr(nn_ctx), _ptr(Z), _ptr(U), _ptr(cost), _ptr(viol))

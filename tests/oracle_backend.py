@@ -14,6 +14,7 @@ class OracleBackend:
         self.cold = c_oracle.COracle(self.P, term, **options)
         warm = dict(options); warm.update(mu0=1e-4, y_init_min=1e-3)      # igt_params mu0_warm / y_init_min_warm
         self.warm = c_oracle.COracle(self.P, term, **warm)
+        self.plain = c_oracle.COracle(self.P, **options)                  # 'mpc' cost: evaluate() without a value-network context
 
     def solve_batch(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None):
         co = self.warm if u_init is not None else self.cold
@@ -21,6 +22,7 @@ class OracleBackend:
         return dict(x=r["Z"], u=r["U"], cost=r["cost"], viol=r["viol"], status=r["status"], iters=r["iters"])
 
     def evaluate(self, x0, u_prev, curv, obs_xy, u, nn_ctx=None):
-        Z = self.cold.rollout(x0, u, curv)
-        cost, viol = self.cold.eval(x0, u_prev, curv, obs_xy, Z, u)
+        co = self.cold if nn_ctx is not None else self.plain
+        Z = co.rollout(x0, u, curv)
+        cost, viol = co.eval(x0, u_prev, curv, obs_xy, Z, u, nn_ctx=nn_ctx)
         return dict(cost=cost, viol=viol, x=Z)
