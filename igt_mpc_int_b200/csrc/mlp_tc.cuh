@@ -156,7 +156,9 @@ __device__ __forceinline__ void mlp_tc_eval(MlpTcCtx &c, bool valid, float sN, f
     float acc[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
     const uint32_t idesc = tc_idesc_m128_n64();
     uint8_t *sA = c.smem + TC_SMEM_A, *sW = c.smem + TC_SMEM_W;
-    for (int g = 0; g < 2; g++) {
+    // the two groups of 128 rows take turns; a group without work is skipped (CTA-uniform)
+    const int g_lo = __syncthreads_or(valid && grp == 0) ? 0 : 1, g_hi = __syncthreads_or(valid && grp == 1) ? 2 : 1;
+    for (int g = g_lo; g < g_hi; g++) {
         for (int nh = 0; nh < 2; nh++) {
             for (int r = 0; r < 6; r++) {
                 // ---- this group's threads write row r of the layer-1 output (bf16 hi/mid/lo) ----

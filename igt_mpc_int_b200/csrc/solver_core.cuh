@@ -54,6 +54,7 @@ constexpr int NGE = 8, NHE = 22;
 // buffer `cur` goes to the j-th buffer other than `cur`, so that the usual case (first candidate
 // accepted) keeps toggling between buffers 0 and 1 and the speculative buffers stay cold.
 constexpr int MAX_ALPHA = 6, NBUF = MAX_ALPHA + 1;
+constexpr int NTC = 8;     // per-candidate scalars: finite flag, cost, terminal value term and its 5 derivatives
 IGT_HD constexpr int cand_buf(int cur, int j) { return j < cur ? j : j + 1; }
 constexpr int MAX_MLP_LAYERS = 5;
 constexpr int N_GUESS = 5;
@@ -106,7 +107,7 @@ struct WsLayout {
         oHl = o;   o += NHE * (N + 1);
         oTr = o;   o += NBUF * 3 * (N + 1);  // per-node results of a trial step, see node_phase3
         oDu = o;   o += NBUF * 2 * N;        // control change of a trial step (exact, not new - old)
-        oTc = o;   o += NBUF * 2;            // per-candidate rollout results: finite flag, cost
+        oTc = o;   o += NBUF * NTC;          // per-candidate rollout results: finite flag, cost, value term (6)
         total = o;
     }
 };
@@ -141,7 +142,7 @@ struct Ws {
     IGT_HD T &Hl(int k, int e) const { return at(L.oHl + k * NHE + e); }
     IGT_HD T &Tr(int b, int k, int e) const { return at(L.oTr + (b * (L.N + 1) + k) * 3 + e); }
     IGT_HD T &Du(int b, int k, int i) const { return at(L.oDu + (b * L.N + k) * 2 + i); }
-    IGT_HD T &Tc(int b, int e) const { return at(L.oTc + b * 2 + e); }
+    IGT_HD T &Tc(int b, int e) const { return at(L.oTc + b * NTC + e); }
 };
 
 // problem inputs / outputs: batch-major AoS arrays exactly as the C ABI receives them
@@ -1481,13 +1482,23 @@ struct Solver {
     }
 
     // judge candidates 0 .. nj-1 in the order sequential halving would try them
-    IGT_HD void accept_trials(int nj)
+    // (stored: the terminal value terms of the candidates were evaluated CTA-wide on the tensor cores and
+    // left in Tc(buffer, 2..7), see tc_candidates)
+    IGT_HD void accept_trials(int nj, bool stored = false)
     {
         int jacc = -1, tried = 0;
         for (int j = 0; j < nj && jacc < 0; j++) {
             trials++; tried++;
             collect_trial(j);
-            if (trial_ok) terminal_of(cand_buf(cur, j), tcand, true);
+            if (trial_ok) {
+                const int nb = cand_buf(cur, j);
+                if (stored) {
+                    tcand.V = w.Tc(nb, 2); tcand.gs = w.Tc(nb, 3); tcand.gv = w.Tc(nb, 4);
+                    tcand.Hss = w.Tc(nb, 5); tcand.Hsv = w.Tc(nb, 6); tcand.Hvv = w.Tc(nb, 7);
+                } else {
+                    terminal_of(nb, tcand, true);
+                }
+            }
             if (trial_passes()) jacc = j;
         }
         finish_trials(jacc, tried);
@@ -1720,9 +1731,10 @@ __device__ long long g_mid_t;            // debug: end of the rollouts of CTA 0'
 // in one pass instead of up to n_alpha.  Returns the number of candidates per problem.
 template <typename T>
 __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
-                                               long bound, const Solver<T> &sv, NodeList<T> &nl, bool speculate)
+                                               long bound, const Solver<T> &sv, NodeList<T> &nl, bool speculate, int &n_out)
 {
     const int n = cta_list_build(need, bound, sv, nl);
+    n_out = n;
     if (n == 0) { IGT_MID_TICK(); return 1; }                     // CTA-uniform
     int n_spec = 1;
     if (speculate) { n_spec = (int)blockDim.x / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
@@ -1732,6 +1744,40 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
     phase_items<T, 4>(ws_base, &nl, n, n_spec);
     __syncthreads();
     return n_spec;
+}
+
+// gt_mpc with the tensor-core value term: the terminal values (and derivatives) of all n * n_spec
+// line-search candidates of the CTA in one CTA-wide evaluation -- thread t takes candidate t / n of the
+// t % n-th listed problem -- left in Tc(candidate buffer, 2..7) for the owner's accept_trials.
+template <typename T>
+__device__ __forceinline__ void tc_candidates(const DevParams<T> &P, const ProbIO &io, T *ws_base, const WsLayout &L,
+                                              const NodeList<T> &nl, int n, int n_spec, MlpTcCtx &tc)
+{
+    if (n == 0) return;                                            // CTA-uniform
+    const int t = threadIdx.x, q = t % n, j = t / n;
+    bool valid = t < n * n_spec && j < P.n_alpha - nl.ctx[q].ls;
+    Ws<T> w; w.L = L;
+    int nb = 0;
+    float cx[4] = { 0.f, 0.f, 0.f, 0.f }, o[6], sN = 0.f, vN = 0.f;
+    if (valid) {
+        w.bind(ws_base, nl.slot[q]);
+        nb = cand_buf(nl.ctx[q].cur, j);
+        valid = w.Tc(nb, 0) != T(0);                               // the rollout stayed finite
+    }
+    if (valid) {
+        const long p = (nl.ctx[q].x0p - io.x0) / NZ;
+#pragma unroll
+        for (int i = 0; i < 4; i++) cx[i] = float(io.ctx[p * 4 + i]);
+        sN = float(w.Z(nb, P.N, IS)); vN = float(w.Z(nb, P.N, IV));
+    }
+    if (__syncthreads_or(valid)) {
+        mlp_tc_eval(tc, valid, sN, vN, cx, o);
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) w.Tc(nb, 2 + i) = T(o[i]);
+        }
+    }
+    __syncthreads();
 }
 
 // Optional per-phase cycle counters of the first thread of CTA 0 (build with -DIGT_PHASE_CLOCKS;
@@ -1884,26 +1930,16 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         IGT_TICK(6);
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
-        const int n_spec = trial_phase_cta(P, ws_base, sv.w.L, trying, bound, sv, nl, !TC);
+        int n_try = 0;
+        const int n_spec = trial_phase_cta(P, ws_base, sv.w.L, trying, bound, sv, nl, true, n_try);
 #ifdef IGT_PHASE_CLOCKS
         if (clk_on) { long long m_ = g_mid_t; clk[7] += m_ - clk_t; if (round_i < 512) g_round_ph[round_i][7] += (int)((m_ - clk_t) >> 10); clk_t = m_; }
 #endif
         IGT_TICK(11);
-        if (TC) {
-            // one candidate per pass; its terminal value comes from the tensor cores, CTA-wide
-            if (trying) { sv.trials++; sv.collect_trial(0); }
-            const bool need = trying && sv.trial_ok;
-            if (__syncthreads_or(need)) {
-                const int nb = cand_buf(sv.cur, 0);
-                float cx[4] = { float(sv.ctx[0]), float(sv.ctx[1]), float(sv.ctx[2]), float(sv.ctx[3]) }, o[6];
-                float sN = need ? float(sv.w.Z(nb, P.N, IS)) : 0.f, vN = need ? float(sv.w.Z(nb, P.N, IV)) : 0.f;
-                mlp_tc_eval(*tc, need, sN, vN, cx, o);
-                if (need) term_from_tc(o, sv.tcand);
-            }
-            if (trying) sv.finish_trials(sv.trial_passes() ? 0 : -1, 1);
-        } else if (trying) {
+        if (TC) tc_candidates(P, io, ws_base, sv.w.L, nl, n_try, n_spec, *tc);   // value terms of all candidates, CTA-wide
+        if (trying) {
             const int left = P.n_alpha - sv.ls;
-            sv.accept_trials(n_spec < left ? n_spec : left);
+            sv.accept_trials(n_spec < left ? n_spec : left, TC);
         }
         IGT_TICK(8);
         if (active && sv.done) { sv.write_out(io, p); active = false; atomicSub(sc.in_flight, 1); }

@@ -8,13 +8,20 @@ _lib.LIB_PATH = os.path.abspath(sys.argv[1])
 from igt_mpc_int_b200 import scenarios as S
 from igt_mpc_int_b200.planner import BatchSolver
 B = int(sys.argv[2]); N = 40
+GT = len(sys.argv) > 3 and sys.argv[3] == "gt"          # gt_mpc mode with the random-init value network (tensor-core path)
 pb = S.mid_episode(B, N=N)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 x0, up, cv, ob = t(pb.x0), t(pb.u_prev), t(pb.curv), t(pb.obs)
-s = BatchSolver(N=N)
-out = s.solve_batch_device(x0, up, cv, ob); torch.cuda.synchronize()
+kw = {}
+if GT:
+    import bench
+    s = BatchSolver(N=N, mlp=bench.random_mlp())
+    kw = dict(nn_ctx=t(pb.nn_ctx))
+else:
+    s = BatchSolver(N=N)
+out = s.solve_batch_device(x0, up, cv, ob, **kw); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); out = s.solve_batch_device(x0, up, cv, ob, out=out); e1.record(); torch.cuda.synchronize()
+e0.record(); out = s.solve_batch_device(x0, up, cv, ob, out=out, **kw); e1.record(); torch.cuda.synchronize()
 clk = (C.c_longlong * 16)()
 lib = _lib.load()
 lib.igt_debug_phase_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
