@@ -80,3 +80,27 @@ def test_gt_mpc_solve_matches_oracle(oracle_params, hidden):
         assert np.mean((r2["status"] == 0) == (r["status"] == 0)) > 0.97
         assert np.quantile(relerr(r2["cost"][ok2], r["cost"][ok2]), 0.98) < 1e-4
     s.close()
+
+
+def test_gt_mpc_full_size_batch_properties():
+    """BASELINE config 3 at full size (gt_mpc, 16384 problems, random-init 6-128-128-1 network, tensor-core value
+    term with the speculative line search): rows satisfied to 1e-6, cost reproduced by the fp64 evaluation kernel
+    to the accuracy of the fp32-accurate value term, and bit-identical results for the reversed batch (which
+    candidate lands in which tensor-core row depends on the batch; the result of a row does not)."""
+    from igt_mpc_int_b200.planner import BatchSolver
+    from igt_mpc_int_b200 import scenarios as S
+    term = _term(_net((128, 128)), False)
+    N, B = 40, 16384
+    pb = S.mid_episode(B, N=N, seed=2026)
+    s = BatchSolver(N=N, mlp=_as_dict(term))
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, nn_ctx=pb.nn_ctx)
+    ok = r["status"] == 0
+    assert ok.mean() > 0.88
+    assert np.max(r["viol"][ok]) <= 1e-6
+    idx = np.where(ok)[0][::16]
+    ev = s.evaluate(pb.x0[idx], pb.u_prev[idx], pb.curv[idx], pb.obs[idx], r["u"][idx], nn_ctx=pb.nn_ctx[idx])
+    assert np.max(relerr(ev["cost"], r["cost"][idx])) < 2e-5 and np.max(ev["viol"]) <= 1e-6
+    rr = s.solve_batch(pb.x0[::-1], pb.u_prev[::-1], pb.curv[::-1], pb.obs[::-1], nn_ctx=pb.nn_ctx[::-1])
+    for k in ("status", "iters", "cost", "u"):
+        assert np.array_equal(rr[k][::-1], r[k], equal_nan=True), k
+    s.close()
