@@ -489,21 +489,17 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
         rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * n_slots * esz);
         if (rc) return rc;
     }
-    // scheduler block: [counter, q_head, q_tail, in_flight | queue[n_slots] | save_i | save_t], then the guesses
-    size_t off_queue = 256, off_savei = off_queue + ((size_t)n_slots * 4 + 255) / 256 * 256;
-    size_t off_savet = off_savei + (size_t)n_slots * SAVE_I * 8, off_guess = off_savet + (size_t)n_slots * SAVE_T * 8;
+    // scheduler block (the work counter), then the cold-start guesses
+    const size_t off_guess = 256;
     rc = grow(h, &h->guess, &h->guess_bytes, off_guess + (size_t)B * h->prm.N * 2 * sizeof(double));
     if (rc) return rc;
     char *sb = (char *)h->guess;
     Sched sc;
-    sc.counter = (unsigned long long *)sb; sc.q_head = (int *)(sb + 8); sc.q_tail = (int *)(sb + 12);
-    sc.in_flight = (int *)(sb + 16); sc.queue = (int *)(sb + off_queue);
-    sc.save_i = (long long *)(sb + off_savei); sc.save_t = (double *)(sb + off_savet);
+    sc.counter = (unsigned long long *)sb;
     double *guess = (double *)(sb + off_guess);
     rc = upload_params(h, st, !f64, f64);
     if (rc) return rc;
     CK(cudaMemsetAsync(sb, 0, 256, st));
-    CK(cudaMemsetAsync(sc.queue, 0xFF, (size_t)n_slots * 4, st));
     ProbIO io = { x0, u_prev, curv, obs_xy, nn_ctx, u_init, x, u, cost, viol, status, iters };
     if (!u_init) {
         int gbs = 128, ggs = (B + gbs - 1) / gbs;

@@ -1578,55 +1578,19 @@ IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, l
 }
 
 #ifdef __CUDACC__
-// Scheduler state shared by all lanes of a solve launch (device memory, zeroed / -1-filled by the
-// host before the launch).
+// Scheduler state shared by all lanes of a solve launch (device memory, zeroed by the host before it).
 struct Sched {
     unsigned long long *counter;   // next fresh problem
-    int *q_head, *q_tail;          // resume queue of donated problems (slot ids)
-    int *in_flight;                // problems fetched and not yet finished
-    int *queue;                    // [n_slots], -1 = not yet published
-    double *save_t;                // [n_slots][SAVE_T]
-    long long *save_i;             // [n_slots][SAVE_I]
 };
-constexpr int SAVE_T = 20, SAVE_I = 8;
-constexpr int DONATE_THRESH = 16;  // a warp with this many or fewer busy lanes hands its problems over
-constexpr int DONATE_MIN_ITERS = 3;
-
-template <typename T>
-__device__ __forceinline__ void save_state(const Solver<T> &sv, const Sched &sc, long slot, long p)
-{
-    double *t = sc.save_t + slot * SAVE_T;
-    long long *q = sc.save_i + slot * SAVE_I;
-    q[0] = p; q[1] = sv.cur; q[2] = sv.status; q[3] = sv.iters; q[4] = sv.ls; q[5] = sv.need_back; q[6] = sv.trials;
-    t[0] = sv.mu; t[1] = sv.reg; t[2] = sv.alpha; t[3] = sv.Jcur; t[4] = sv.lgcur; t[5] = sv.thetacur; t[6] = sv.phi;
-    t[7] = sv.stat; t[8] = sv.rp; t[9] = sv.s_max; t[10] = sv.sy_min; t[11] = sv.sy_max;
-    t[12] = sv.tcur.V; t[13] = sv.tcur.gs; t[14] = sv.tcur.gv; t[15] = sv.tcur.Hss; t[16] = sv.tcur.Hsv; t[17] = sv.tcur.Hvv;
-}
-
-template <typename T>
-__device__ __forceinline__ long restore_state(Solver<T> &sv, const Sched &sc, long slot, const ProbIO &io)
-{
-    const double *t = sc.save_t + slot * SAVE_T;
-    const long long *q = sc.save_i + slot * SAVE_I;
-    long p = q[0];
-    sv.cur = (int)q[1]; sv.status = (int)q[2]; sv.iters = (int)q[3]; sv.ls = (int)q[4]; sv.need_back = (int)q[5]; sv.trials = (int)q[6];
-    sv.done = false;
-    sv.mu = T(t[0]); sv.reg = T(t[1]); sv.alpha = T(t[2]); sv.Jcur = T(t[3]); sv.lgcur = T(t[4]); sv.thetacur = T(t[5]);
-    sv.phi = T(t[6]); sv.stat = T(t[7]); sv.rp = T(t[8]); sv.s_max = T(t[9]); sv.sy_min = T(t[10]); sv.sy_max = T(t[11]);
-    sv.tcur.V = T(t[12]); sv.tcur.gs = T(t[13]); sv.tcur.gv = T(t[14]); sv.tcur.Hss = T(t[15]); sv.tcur.Hsv = T(t[16]);
-    sv.tcur.Hvv = T(t[17]);
-    sv.load_inputs(io, p, io.ctx != nullptr);
-    return p;
-}
 
 // Persistent-lane driver: every thread owns one workspace slot and keeps pulling problems from
 // a global counter until none are left.  All 32 lanes of a warp walk the phases of an iteration
 // (backward sweeps, forward trial, acceptance) together, each lane on its own problem and at
 // its own iteration count, so a slow or failing problem delays only its own lane.
-// Tail balancing: once no fresh problems remain, a warp left with <= DONATE_THRESH busy lanes
-// parks its problems (iterate in the slot's workspace, scalars in save_*) in a resume queue;
-// fully idle warps adopt up to 32 parked problems at a time, so the stragglers of many warps are
-// packed into few full warps.
+// (An earlier version handed the stragglers of the tail over to idle warps of other CTAs through a
+// resume queue.  Since the node phases and the line-search candidates of a thin CTA are dealt out over
+// all of its threads anyway, packing stragglers no longer shortens a round -- its length is the serial
+// latency of one problem's sweeps -- and the queue polling cost 2 %: removed.)
 template <typename T>
 __device__ __forceinline__ void term_from_tc(const float *o, TermVal<T> &t)
 {
@@ -1804,12 +1768,11 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
     sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     // only the first `quota` threads of a CTA fetch fresh problems, so that a batch smaller than the
     // machine is spread over all SMs; the other threads still work in the CTA-wide phases
     bool active = false, exhausted = (int)threadIdx.x >= quota;
-    long p = -1, bound = slot;
-    int since_adopt = DONATE_MIN_ITERS;
+    long p = -1;
+    const long bound = slot;
     if (TC) sv.phi_noise = T(3e-7);
 #ifdef IGT_PHASE_CLOCKS
     const bool clk_on = blockIdx.x == 0 && threadIdx.x == 0;
@@ -1827,16 +1790,13 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
             p = (long)atomicAdd(sc.counter, 1ULL);
             if (p >= B) exhausted = true;
             else {
-                if (bound != slot) { bound = slot; sv.w.bind(ws_base, slot); }
                 const double *u_src = (io.u_init ? io.u_init : guess) + p * P.N * 2;
-                atomicAdd(sc.in_flight, 1);
                 if (sv.init(io, p, io.ctx != nullptr, u_src, io.u_init != nullptr)) {
                     if (!TC) sv.terminal_of(sv.cur, sv.tcur, true);
                     active = true;
                     fresh = true;
                 } else {
                     sv.write_out(io, p);
-                    atomicSub(sc.in_flight, 1);
                 }
             }
         }
@@ -1848,49 +1808,8 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
                 if (fresh) term_from_tc(o, sv.tcur);
             }
         }
-        const bool no_new = __all_sync(FULL, exhausted);
-        int n_act = __popc(__ballot_sync(FULL, active));
-        bool wants_exit = false;
-        if (no_new) {
-            if (n_act > 0 && n_act <= DONATE_THRESH && since_adopt >= DONATE_MIN_ITERS) {
-                if (active) {                       // park: publish this lane's problem
-                    save_state(sv, sc, bound, p);
-                    __threadfence();
-                    int idx = atomicAdd(sc.q_tail, 1);
-                    atomicExch(sc.queue + idx, (int)bound);
-                    active = false;
-                }
-                n_act = 0;
-            }
-            if (n_act == 0) {
-                // adopt up to 32 parked problems; with nothing parked and nothing in flight, leave
-                int base = 0, n = 0, fl = 0;
-                if (lane == 0) {
-                    int head = *(volatile int *)sc.q_head;
-                    for (;;) {
-                        int tail = *(volatile int *)sc.q_tail;
-                        if (head >= tail) break;
-                        int want = min(32, tail - head);
-                        int old = atomicCAS(sc.q_head, head, head + want);
-                        if (old == head) { base = head; n = want; break; }
-                        head = old;
-                    }
-                    fl = *(volatile int *)sc.in_flight;
-                }
-                base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0); fl = __shfl_sync(FULL, fl, 0);
-                if (n == 0) wants_exit = (fl == 0);
-                if (lane < n) {
-                    int s_id;
-                    while ((s_id = *(volatile int *)(sc.queue + base + lane)) < 0) __nanosleep(100);
-                    __threadfence();               // also drops stale L1 lines of the adopted slot
-                    bound = s_id;
-                    sv.w.bind(ws_base, bound);
-                    p = restore_state(sv, sc, bound, io);
-                    active = true;
-                }
-                if (n > 0) since_adopt = 0;
-            }
-        }
+        // a warp is finished once its lanes can fetch no more and none of them is busy
+        const bool wants_exit = __all_sync(FULL, exhausted && !active);
 #ifdef IGT_PHASE_CLOCKS
         const int cta_busy = __syncthreads_count(active);
         if (clk_on && round_i < 512) {
@@ -1902,7 +1821,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         const int cta_busy = __syncthreads_or(active);
 #endif
         if (__syncthreads_and(wants_exit)) break;
-        if (!cta_busy) { __nanosleep(2000); since_adopt++; IGT_TICK(9); continue; }   // nothing to do here: poll the queue gently
+        if (!cta_busy) { IGT_TICK(9); continue; }               // (only while other warps still fetch)
         IGT_TICK(0);
         // ---- phase 1: backward pass = CTA-wide node phases between the per-problem sweeps ----
         const bool back = active && sv.need_back;
@@ -1942,8 +1861,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
             sv.accept_trials(n_spec < left ? n_spec : left, TC);
         }
         IGT_TICK(8);
-        if (active && sv.done) { sv.write_out(io, p); active = false; atomicSub(sc.in_flight, 1); }
-        since_adopt++;
+        if (active && sv.done) { sv.write_out(io, p); active = false; }
         IGT_TICK(10);
     }
 #ifdef IGT_PHASE_CLOCKS
