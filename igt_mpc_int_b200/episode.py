@@ -65,15 +65,6 @@ def reference_episode_specs(scenarios=range(1, 9), sample=0, seed=2026):
     return specs
 
 
-def _route_xy(s, route):
-    return G.frenet2global(float(s), route, exit_coord=G.EXIT_COORD.get(route))[:2]
-
-
-def _ca_step(s, v, a, dt):
-    """One constant-acceleration predictor step, constant_acceleration_model.py:69-71."""
-    return s + v * dt + 0.5 * a * dt * dt, min(max(v + a * dt, V_PRED_MIN), V_PRED_MAX)
-
-
 def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_latency=False, mode="mpc"):
     """mode 'gt_mpc' (the solver must have been given the value network): previous input (0, 0) instead of
     (0.1, 0) (evaluate.py:171 / :419); the first forecast assumes a = 0.09 (i + 1) for vehicle i
@@ -100,33 +91,54 @@ def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_la
     z_cl[:, :, 0] = z.reshape(E, 2, 7)
     prev_x = np.zeros((B, N + 1, 7)); prev_u = np.zeros((B, N, 2)); prev_ok = np.zeros(B, dtype=bool)
     lat = []
+    route_of = [routes[b // 2][b % 2] for b in range(B)]
+    groups = {r: np.array([b for b in range(B) if route_of[b] == r]) for r in sorted(set(route_of))}
+
+    def route_xy(s):
+        """lane-centre (x, y) of every vehicle's arc length(s): s[B] or s[B, K]"""
+        x = np.empty_like(s); y = np.empty_like(s)
+        for r, idx in groups.items():
+            x[idx], y[idx] = G.frenet2global_xy(s[idx], r, exit_coord=G.EXIT_COORD.get(r))
+        return x, y
+
+    def ca_step(s, v, a):
+        """one constant-acceleration predictor step, constant_acceleration_model.py:69-71 (vectorised)"""
+        return s + v * dt + 0.5 * a * dt * dt, np.minimum(np.maximum(v + a * dt, V_PRED_MIN), V_PRED_MAX)
+
     for t in range(steps):
-        # ---- forecasts of every vehicle (N+1 points: x, y, s, v) ----
+        # ---- forecasts of every vehicle (N+1 points: x, y, s, v), all vehicles at once ----
         fc = np.zeros((B, N + 1, 4))
-        for b in range(B):
-            route = routes[b // 2][b % 2]
-            if t > 0 and prev_ok[b]:
-                # V2V: the previous plan shifted by one + one constant-acceleration step (utils.py:339-352)
-                fc[b, :N, 0] = prev_x[b, 1:, 0]; fc[b, :N, 1] = prev_x[b, 1:, 1]
-                fc[b, :N, 2] = prev_x[b, 1:, 2]; fc[b, :N, 3] = prev_x[b, 1:, 5]
-                sN, vN = prev_x[b, N, 2], prev_x[b, N, 5]
-                s1, v1 = _ca_step(sN, vN, prev_u[b, N - 1, 0], dt)
-                if v1 > 5:
-                    s1, v1 = _ca_step(sN, vN, 0.0, dt)
-                fc[b, N] = (*_route_xy(s1, route), s1, v1)
-            else:
-                s, v, a = z[b, 2], z[b, 5], u_prev[b, 0]
-                if gt and t == 0:
-                    a = 0.09 * (b % 2 + 1)                                                 # evaluate.py:207-210
-                fc[b, 0] = (z[b, 0], z[b, 1], s, v)
-                for k in range(N):
-                    s, v = _ca_step(s, v, a, dt)
-                    fc[b, k + 1] = (*_route_xy(s, route), s, v)
-        # ---- per-vehicle obstacle = the other vehicle's forecast, filtered (utils.py:365-388) ----
-        obs = np.zeros((B, N + 1, 2))
-        for b in range(B):
-            o = b ^ 1
-            obs[b] = G.filter_obstacle(fc[b, 0, :2], z[b, 6], fc[o, :, :2])
+        # constant-acceleration forecast from the current state (constant_acceleration_model.py:18-82)
+        a0 = u_prev[:, 0].copy()
+        if gt and t == 0:
+            a0 = 0.09 * (np.arange(B) % 2 + 1)                                             # evaluate.py:207-210
+        sk = np.empty((B, N + 1)); vk = np.empty((B, N + 1))
+        sk[:, 0], vk[:, 0] = z[:, 2], z[:, 5]
+        for k in range(N):
+            sk[:, k + 1], vk[:, k + 1] = ca_step(sk[:, k], vk[:, k], a0)
+        fc[:, :, 0], fc[:, :, 1] = route_xy(sk)
+        fc[:, 0, 0], fc[:, 0, 1] = z[:, 0], z[:, 1]
+        fc[:, :, 2], fc[:, :, 3] = sk, vk
+        if t > 0 and prev_ok.any():
+            # V2V: a vehicle that solved at t-1 is forecast by its previous plan shifted by one + one
+            # constant-acceleration step (redone with a = 0 if that exceeds v = 5), utils.py:339-352
+            v2v = np.where(prev_ok)[0]
+            fc[v2v, :N, 0] = prev_x[v2v, 1:, 0]; fc[v2v, :N, 1] = prev_x[v2v, 1:, 1]
+            fc[v2v, :N, 2] = prev_x[v2v, 1:, 2]; fc[v2v, :N, 3] = prev_x[v2v, 1:, 5]
+            sN, vN = prev_x[:, N, 2], prev_x[:, N, 5]
+            s1, v1 = ca_step(sN, vN, prev_u[:, N - 1, 0])
+            s1b, v1b = ca_step(sN, vN, 0.0)
+            over = v1 > 5
+            s1, v1 = np.where(over, s1b, s1), np.where(over, v1b, v1)
+            x1, y1 = route_xy(s1)
+            fc[v2v, N, 0], fc[v2v, N, 1], fc[v2v, N, 2], fc[v2v, N, 3] = x1[v2v], y1[v2v], s1[v2v], v1[v2v]
+        # ---- per-vehicle obstacle = the other vehicle's forecast; all of it moves to (-20, -20) if the other
+        #      vehicle is behind the ego (negative dot product with the ego heading), utils.py:365-388 ----
+        other = np.arange(B) ^ 1
+        obs = fc[other][:, :, :2].copy()
+        dx, dy = obs[:, 0, 0] - fc[:, 0, 0], obs[:, 0, 1] - fc[:, 0, 1]
+        behind = dx * np.cos(z[:, 6]) + dy * np.sin(z[:, 6]) < 0
+        obs[behind] = -20.0
         # ---- solve: warm-started vehicles and cold ones in two batched calls ----
         t0 = time.perf_counter()
         u_init = np.concatenate([prev_u[:, 1:], prev_u[:, -1:]], axis=1)                   # utils.py:362

@@ -136,6 +136,34 @@ def frenet2global(s, route, ey=0.0, W=ROAD_WIDTH, L=ROAD_LENGTH, ca=CA_RADIUS, e
     return x, y, th
 
 
+def frenet2global_xy(s, route, W=ROAD_WIDTH, L=ROAD_LENGTH, ca=CA_RADIUS, exit_coord=None):
+    """`frenet2global` (lane centre, ey = 0) for an array of arc lengths: s[...] -> x[...], y[...]."""
+    s = np.asarray(s, dtype=np.float64)
+    x0, y0, th0 = start_pose(route[0], W, L, ca)
+    t0 = (math.cos(th0), math.sin(th0))
+    n0 = (-t0[1], t0[0])
+    sgn = turn_sign(route)
+    if sgn == 0:
+        return x0 + s * t0[0], y0 + s * t0[1]
+    b0, b1, K = curvature_params(route, W, L, ca)
+    r = 1.0 / abs(K)
+    cx, cy = x0 + b0 * t0[0] + sgn * r * n0[0], y0 + b0 * t0[1] + sgn * r * n0[1]
+    phi = (s - b0) / r
+    xa = cx + r * (np.sin(phi) * t0[0] - sgn * np.cos(phi) * n0[0])
+    ya = cy + r * (np.sin(phi) * t0[1] - sgn * np.cos(phi) * n0[1])
+    t1 = (sgn * n0[0], sgn * n0[1])
+    xe = cx + r * t0[0] + (s - b1) * t1[0]
+    ye = cy + r * t0[1] + (s - b1) * t1[1]
+    if exit_coord is not None:
+        if abs(t1[0]) < 0.5:
+            xe = np.full_like(s, exit_coord)
+        else:
+            ye = np.full_like(s, exit_coord)
+    x = np.where(s < b0, x0 + s * t0[0], np.where(s <= b1, xa, xe))
+    y = np.where(s < b0, y0 + s * t0[1], np.where(s <= b1, ya, ye))
+    return x, y
+
+
 def scenario_routes(sc, rotation, order):
     """Route pair of scenario `sc` (1..8): `rotation` picks one of the four rotated pairs
     (utils.py:177-179 does this with an unseeded random.choice) and `order` the agent order

@@ -81,3 +81,11 @@ def test_reference_track_generator_matches_reference_output(golden):
     # a vehicle that starts further down the road gets the track from its nearest sample on
     d = RT.reference_dict('12', 7.3, 2.8)
     assert abs(d['x'][0] - 7.5) < 1e-12 and d['K'][0] == 0.0 and len(d['s']) == 151
+
+
+def test_vectorised_frenet2global_matches_scalar():
+    for r in G.ROUTES:
+        s = np.linspace(0, 75, 301)
+        x, y = G.frenet2global_xy(s, r, exit_coord=G.EXIT_COORD.get(r))
+        ref = np.array([G.frenet2global(float(si), r, exit_coord=G.EXIT_COORD.get(r))[:2] for si in s])
+        assert np.abs(x - ref[:, 0]).max() < 1e-12 and np.abs(y - ref[:, 1]).max() < 1e-12, r
