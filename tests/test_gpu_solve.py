@@ -226,3 +226,58 @@ def test_short_horizons_full_path(oracle_params, N):
     assert np.max(np.abs(r["u"][both] - o["U"][both])) < 1e-3
     assert np.max(r["viol"][both]) <= 1e-6
     s.close()
+
+
+def _vs_oracle(s, P, pb, frac=0.9):
+    from oracle import c_oracle
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    o = c_oracle.COracle(P, max_iter=s.params.max_iter, max_trials=s.params.max_trials).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    both = (o["status"] == 0) & (r["status"] == 0)
+    assert np.mean((o["status"] == 0) == (r["status"] == 0)) >= 0.99
+    assert both.mean() >= frac
+    assert np.max(relerr(r["cost"][both], o["cost"][both])) < 1e-4
+    assert np.max(np.abs(r["u"][both] - o["U"][both])) < 1e-3
+    assert np.max(r["viol"][both]) <= 1e-6
+    return r
+
+
+def test_reference_initial_condition_distribution(oracle_params):
+    """The reference's own start-of-episode distribution (evaluate.py:91-94, :404-419: s0 ~ U(0, 10.7), v0 = 0,
+    u_prev = (0.1, 0)), 2048 problems over scenarios 1-8."""
+    from igt_mpc_int_b200 import scenarios as S
+    s = _solver(40)
+    r = _vs_oracle(s, oracle_params[40], S.episode_start(2048, N=40, seed=2026), frac=0.97)
+    assert np.median(r["iters"][r["status"] == 0]) <= 20
+    s.close()
+
+
+@pytest.mark.parametrize("N", [2, 5, 64])
+def test_extreme_horizons(N):
+    """Shortest and longest horizons igt_create accepts (2 <= N <= 64)."""
+    from igt_mpc_int_b200 import scenarios as S
+    from oracle import nlp
+    base = nlp.Params(N=40)
+    P = nlp.Params(N=N, cinf_A=base.cinf_A, cinf_b=base.cinf_b)
+    s = _solver(N)
+    _vs_oracle(s, P, S.mid_episode(64, N=N, seed=3), frac=0.7)
+    s.close()
+
+
+def test_tiny_and_ragged_batches_and_bad_inputs(oracle_params):
+    """B = 1, 2, 33 (one lane, the closed-loop pair, one warp + 1): the same answers as inside a big batch; a
+    non-finite state comes back with a failure status instead of hanging or poisoning its neighbours."""
+    from igt_mpc_int_b200 import scenarios as S
+    pb = S.mid_episode(64, N=40, seed=11)
+    s = _solver(40)
+    full = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    for B in (1, 2, 33):
+        r = s.solve_batch(pb.x0[:B], pb.u_prev[:B], pb.curv[:B], pb.obs[:B])
+        for k in ("status", "iters", "cost", "u"):
+            assert np.array_equal(r[k], full[k][:B], equal_nan=True), (B, k)
+    x0 = pb.x0.copy(); x0[3, 0] = np.nan; x0[5, 2] = np.inf
+    r = s.solve_batch(x0, pb.u_prev, pb.curv, pb.obs)
+    assert r["status"][3] != 0 and r["status"][5] != 0
+    keep = np.ones(64, dtype=bool); keep[[3, 5]] = False
+    for k in ("status", "iters", "cost"):
+        assert np.array_equal(r[k][keep], full[k][keep], equal_nan=True), k
+    s.close()
