@@ -62,6 +62,18 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws,
     if (TC) mlp_tc_teardown(tc);
 }
 
+// Latency path for batches of at most one problem per SM (the closed-loop step: B = 2): one CTA per problem,
+// its whole workspace in shared memory (stride-1 layout), so the sweeps of the problem's one owner thread run at
+// shared-memory latency instead of an L2 round trip per stage; the node phases and the line-search candidates
+// are dealt out over the CTA's 256 threads as in the throughput kernel.  Same code, same arithmetic, same results.
+template <typename T>
+__global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_small_kernel(ProbIO io, long B, Sched sc, const double *guess)
+{
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const DevParams<T> &P = ConstP<T>::get();
+    solve_persistent<T, false, 1>(P, io, reinterpret_cast<T *>(dyn_smem), 0, B, sc, guess, (T *)nullptr, 0, nullptr, 1);
+}
+
 // fp32 rollout with Kahan-compensated accumulation of the RK4 increments (x, y, s reach ~50 m
 // while one sub-step adds ~0.1 m; plain fp32 accumulation loses the 1e-5 target on ~0.5 % of
 // rollouts).  One problem per thread; outputs are AoS as the ABI promises.
@@ -252,6 +264,7 @@ struct igt_handle {
     bool has_mlp = false;
     MlpTcWeights tc = {};              // tensor-core copy of the value network (6-128-128-1 only)
     int use_tc = 1;                    // igt_set_option("tensor_core_mlp", 0) forces the CUDA-core value term
+    int use_small = 1;                 // igt_set_option("latency_path", 0) keeps small batches on the throughput kernel
     int mlp_width = 0;
     std::vector<void *> mlp_bufs;      // device weight buffers (both precisions)
     void *ws = nullptr; size_t ws_bytes = 0;
@@ -473,6 +486,9 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     const bool f64 = h->prm.precision == IGT_PREC_F64;
     WsLayout L; L.init(h->prm.N, h->prm.n_cinf);
     size_t esz = f64 ? 8 : 4;
+    // latency path: at most one problem per SM and a workspace that fits shared memory next to the work lists
+    const size_t small_smem = (size_t)L.total * esz;
+    const bool small = h->use_small && !nn_ctx && B <= h->n_sm && small_smem <= 200 * 1024;
     // persistent lanes: one CTA of SOLVE_BLOCK threads per SM.  A batch smaller than the machine is spread
     // over all SMs, a whole number of warps each: `quota` threads per CTA fetch problems, the rest of
     // the CTA only helps in the CTA-wide phases (and adopts stragglers in the tail).
@@ -483,7 +499,7 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     int quota = (int)((per_cta + 31) / 32 * 32);
     if (quota > bs) quota = bs;
     long n_slots = n_cta * bs;
-    int rc = grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * n_slots * esz);
+    int rc = small ? IGT_OK : grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * n_slots * esz);
     if (rc) return rc;
     if (nn_ctx) {
         rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * n_slots * esz);
@@ -509,7 +525,15 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     }
     int gs = (int)(n_slots / bs);
     const bool use_tc = nn_ctx && h->tc.enabled && h->use_tc;
-    if (use_tc) {
+    if (small) {
+        if (f64) {
+            CK(cudaFuncSetAttribute(solve_small_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+            solve_small_kernel<double><<<B, bs, small_smem, st>>>(io, B, sc, guess);
+        } else {
+            CK(cudaFuncSetAttribute(solve_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+            solve_small_kernel<float><<<B, bs, small_smem, st>>>(io, B, sc, guess);
+        }
+    } else if (use_tc) {
         if (f64) {
             CK(cudaFuncSetAttribute(solve_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
             solve_kernel<double, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota);
@@ -696,6 +720,7 @@ int igt_set_option(igt_handle *h, const char *name, double value)
 {
     if (!h || !name) return IGT_EINVAL;
     if (strcmp(name, "tensor_core_mlp") == 0) { h->use_tc = value != 0.0; return IGT_OK; }
+    if (strcmp(name, "latency_path") == 0) { h->use_small = value != 0.0; return IGT_OK; }
     h->err = std::string("igt_set_option: unknown option ") + name;
     return IGT_EINVAL;
 }

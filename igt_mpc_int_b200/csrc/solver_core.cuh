@@ -116,16 +116,18 @@ struct WsLayout {
 //   base[(q / 32) * total * 32 + e * 32 + (q % 32)]
 // so the 32 lanes of a warp touch 32 consecutive words for every element, and every element
 // offset that is a compile-time constant folds into the load/store immediate.
-template <typename T>
+// STRIDE 1 is the latency path for batches of at most one problem per SM: the workspace of the CTA's one
+// problem lives in shared memory, contiguously (bind ignores the slot, nothing is prefetched).
+template <typename T, int STRIDE = 32>
 struct Ws {
     T *wb;          // base + (slot / 32) * total * 32 + slot % 32
     WsLayout L;
-    IGT_HD void bind(T *base, long slot) { wb = base + (slot / 32) * (long)L.total * 32 + (slot % 32); }
-    IGT_HD T &at(int e) const { return wb[e * 32]; }
+    IGT_HD void bind(T *base, long slot) { wb = STRIDE == 32 ? base + (slot / 32) * (long)L.total * 32 + (slot % 32) : base; }
+    IGT_HD T &at(int e) const { return wb[e * STRIDE]; }
     IGT_HD void pf(int e) const
     {
 #ifdef __CUDA_ARCH__
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + e * 32));
+        if (STRIDE == 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + e * 32));
 #endif
     }
     IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ[b] + k * NZ + i); }
@@ -695,8 +697,8 @@ struct NodeCtx {
     int cur, second_order, ls;
 };
 
-template <typename T>
-IGT_HD void node_load(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k, T *z, T *up, T *u)
+template <typename T, typename W>
+IGT_HD void node_load(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, int k, T *z, T *up, T *u)
 {
     const int b = c.cur;
 #pragma unroll
@@ -709,8 +711,8 @@ IGT_HD void node_load(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c
 // Node phase 1 (independent of the barrier parameter and of the adjoint): sensitivities of stage k
 // and the row summaries the adjoint sweep needs -- sum of g * s per gradient entry, and the node's
 // share of the residual norms (primal residual, largest multiplier, min / max of s * y).
-template <typename T>
-IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k)
+template <typename T, typename W>
+IGT_HD void node_phase1(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, int k)
 {
     const int N = P.N, b = c.cur;
     const int o = row_off(N, P.n_cinf, k);
@@ -755,8 +757,8 @@ IGT_HD void node_phase1(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
 // Node phase 2 (after the barrier update and the adjoint sweep): the rows' share of the perturbed
 // KKT system of node k -- gradient sum of g * (s + (s c + mu) / y), Hessian sum of (s / y) g g' plus
 // s * Hess(c) for the collision row -- and the dynamics second-order term dt * Hess(lambda_{k+1} . f).
-template <typename T>
-IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k)
+template <typename T, typename W>
+IGT_HD void node_phase2(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, int k)
 {
     const int N = P.N, b = c.cur;
     const T mu = c.mu;
@@ -810,8 +812,8 @@ IGT_HD void node_phase2(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
 // Closed-loop nonlinear rollout of candidate j of the line search (step alpha / 2^j) from the
 // current iterate into buffer cand_buf(cur, j): controls and states only; the rows of the trial
 // point are evaluated by node_phase3.  Tc(buffer, .) = (1 if the rollout stayed finite, cost).
-template <typename T>
-IGT_HD void rollout_item(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int j)
+template <typename T, typename W>
+IGT_HD void rollout_item(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, int j)
 {
     const int N = P.N, b = c.cur, nb = cand_buf(c.cur, j);
     T alpha = c.alpha;
@@ -860,8 +862,8 @@ IGT_HD void rollout_item(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T>
 // along the step actually taken (d w_k = new - old iterate), the fraction-to-boundary test, and the
 // node's share of the infeasibility and of the barrier sum at the new point.
 // Tr(buffer, k, .) = (sum |c + y|, sum log y, 1 if the boundary rule failed).
-template <typename T>
-IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> &c, int k, int j)
+template <typename T, typename W>
+IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, int k, int j)
 {
     const int N = P.N, b = c.cur, nb = cand_buf(c.cur, j);
     if (w.Tc(nb, 0) == T(0)) return;                            // the rollout left the finite range
@@ -921,10 +923,10 @@ IGT_HD void node_phase3(const DevParams<T> &P, const Ws<T> &w, const NodeCtx<T> 
 }
 
 // ------------------------------------------------------------------ the solver ---------
-template <typename T>
+template <typename T, typename W = Ws<T>>
 struct Solver {
     const DevParams<T> &P;
-    Ws<T> w;
+    W w;
     T x0[NZ], uprev[2], curv[3], ctx[4];
     const double *obs;        // this problem's [N+1][2] forecast (AoS, read-only)
     const double *x0p;        // this problem's x0[7] in the caller's array
@@ -1619,8 +1621,8 @@ struct NodeList {                    // shared-memory work list of one CTA-wide 
 
 // compact the problems of the CTA that need a phase into the shared work list (slot order is kept,
 // so that neighbouring lanes mostly work on neighbouring slots); returns their number
-template <typename T>
-__device__ __forceinline__ int cta_list_build(bool need, long bound, const Solver<T> &sv, NodeList<T> &nl)
+template <typename T, typename S>
+__device__ __forceinline__ int cta_list_build(bool need, long bound, const S &sv, NodeList<T> &nl)
 {
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -1644,11 +1646,11 @@ __device__ __forceinline__ int cta_list_build(bool need, long bound, const Solve
 // which the translation unit defines.
 template <typename T> struct ConstP;
 
-template <typename T, int PHASE>
+template <typename T, int PHASE, int STRIDE>
 __device__ __noinline__ void phase_items(T *ws_base, const NodeList<T> *nl, int n, int n_spec)
 {
     const DevParams<T> &P = ConstP<T>::get();
-    Ws<T> w; w.L.init(P.N, P.n_cinf);
+    Ws<T, STRIDE> w; w.L.init(P.N, P.n_cinf);
     if (PHASE == 1 || PHASE == 2) {
         const int total = n * (P.N + 1);
         for (int it = threadIdx.x; it < total; it += blockDim.x) {
@@ -1671,12 +1673,12 @@ __device__ __noinline__ void phase_items(T *ws_base, const NodeList<T> *nl, int 
     }
 }
 
-template <typename T, int PHASE>
+template <typename T, int PHASE, int STRIDE, typename S>
 __device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
-                                               long bound, const Solver<T> &sv, NodeList<T> &nl)
+                                               long bound, const S &sv, NodeList<T> &nl)
 {
     const int n = cta_list_build(need, bound, sv, nl);
-    if (n > 0) phase_items<T, PHASE>(ws_base, &nl, n, 1);
+    if (n > 0) phase_items<T, PHASE, STRIDE>(ws_base, &nl, n, 1);
     __syncthreads();
 }
 
@@ -1693,19 +1695,19 @@ __device__ long long g_mid_t;            // debug: end of the rollouts of CTA 0'
 // threads roll out the next halvings at the same time, each into its own iterate buffer, and the
 // owner then takes the first candidate that passes -- the same iterate sequential halving reaches,
 // in one pass instead of up to n_alpha.  Returns the number of candidates per problem.
-template <typename T>
+template <typename T, int STRIDE, typename S>
 __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
-                                               long bound, const Solver<T> &sv, NodeList<T> &nl, bool speculate, int &n_out)
+                                               long bound, const S &sv, NodeList<T> &nl, bool speculate, int &n_out)
 {
     const int n = cta_list_build(need, bound, sv, nl);
     n_out = n;
     if (n == 0) { IGT_MID_TICK(); return 1; }                     // CTA-uniform
     int n_spec = 1;
     if (speculate) { n_spec = (int)blockDim.x / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
-    phase_items<T, 3>(ws_base, &nl, n, n_spec);
+    phase_items<T, 3, STRIDE>(ws_base, &nl, n, n_spec);
     __syncthreads();
     IGT_MID_TICK();
-    phase_items<T, 4>(ws_base, &nl, n, n_spec);
+    phase_items<T, 4, STRIDE>(ws_base, &nl, n, n_spec);
     __syncthreads();
     return n_spec;
 }
@@ -1756,14 +1758,14 @@ __device__ int g_round_ph[512][12];      // per loop pass: kcycles per phase
 #define IGT_TICK(i) do { } while (0)
 #endif
 
-template <typename T, bool TC>
+template <typename T, bool TC, int STRIDE = 32>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
                                                  long slot, long B, const Sched &sc,
                                                  const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc,
                                                  int quota)
 {
     __shared__ NodeList<T> nl;
-    Solver<T> sv(P);
+    Solver<T, Ws<T, STRIDE>> sv(P);
     sv.w.L.init(P.N, P.n_cinf);
     sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
@@ -1825,11 +1827,11 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         IGT_TICK(0);
         // ---- phase 1: backward pass = CTA-wide node phases between the per-problem sweeps ----
         const bool back = active && sv.need_back;
-        node_phase_cta<T, 1>(P, ws_base, sv.w.L, back && sv.need_back == 2, bound, sv, nl);
+        node_phase_cta<T, 1, STRIDE>(P, ws_base, sv.w.L, back && sv.need_back == 2, bound, sv, nl);
         IGT_TICK(1);
         const bool p2 = back && sv.backward_pre();              // adjoint sweep, convergence test, barrier update
         IGT_TICK(2);
-        node_phase_cta<T, 2>(P, ws_base, sv.w.L, p2, bound, sv, nl);
+        node_phase_cta<T, 2, STRIDE>(P, ws_base, sv.w.L, p2, bound, sv, nl);
         IGT_TICK(3);
         if (back && !sv.done) {                                  // Riccati sweep, step bound
 #ifdef IGT_PHASE_CLOCKS
@@ -1850,7 +1852,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
         int n_try = 0;
-        const int n_spec = trial_phase_cta(P, ws_base, sv.w.L, trying, bound, sv, nl, true, n_try);
+        const int n_spec = trial_phase_cta<T, STRIDE>(P, ws_base, sv.w.L, trying, bound, sv, nl, true, n_try);
 #ifdef IGT_PHASE_CLOCKS
         if (clk_on) { long long m_ = g_mid_t; clk[7] += m_ - clk_t; if (round_i < 512) g_round_ph[round_i][7] += (int)((m_ - clk_t) >> 10); clk_t = m_; }
 #endif

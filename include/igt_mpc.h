@@ -145,7 +145,9 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
                        double *out, int use_tensor_cores);
 
 /* Run-time switches.  "tensor_core_mlp" (default 1): evaluate the gt_mpc value term of 6-128-128-1 networks
- * with the tcgen05 kernel inside the solver; 0 = fp64 CUDA-core evaluation (always used for other shapes). */
+ * with the tcgen05 kernel inside the solver; 0 = fp64 CUDA-core evaluation (always used for other shapes).
+ * "latency_path" (default 1): 'mpc'-mode batches of at most one problem per SM (a closed-loop step solves the two
+ * vehicles of an episode) run one CTA per problem with the workspace in shared memory; 0 = throughput kernel. */
 int igt_set_option(igt_handle *h, const char *name, double value);
 
 /* Measured throughput (TFLOP/s, FMA = 2 flops) of dependent-free FMA chains in `precision` on

@@ -281,3 +281,27 @@ def test_tiny_and_ragged_batches_and_bad_inputs(oracle_params):
     for k in ("status", "iters", "cost"):
         assert np.array_equal(r[k][keep], full[k][keep], equal_nan=True), k
     s.close()
+
+
+def test_latency_path_is_bit_identical_to_throughput_kernel():
+    """Batches of at most one problem per SM run one CTA per problem with the workspace in shared memory
+    (igt_set_option "latency_path", default on): the same arithmetic in a different layout -- identical bits,
+    cold and warm-started, fp64 and fp32, including the batch that exactly fills the machine and a short horizon."""
+    import torch
+    from igt_mpc_int_b200 import scenarios as S
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    for N, prec in ((40, "f64"), (10, "f64"), (40, "f32")):
+        pb = S.mid_episode(n_sm // 8 * 8 + 8, N=N, seed=23)
+        s = _solver(N, precision=prec)
+        for B in (1, 2, 33, n_sm):
+            a = (pb.x0[:B], pb.u_prev[:B], pb.curv[:B], pb.obs[:B])
+            out = {}
+            for flag in (0, 1):
+                s.set_option("latency_path", flag)
+                cold = s.solve_batch(*a)
+                warm = s.solve_batch(*a, u_init=np.nan_to_num(cold["u"]))
+                out[flag] = (cold, warm)
+            for i in (0, 1):
+                for k in ("status", "iters", "cost", "viol", "u", "x"):
+                    assert np.array_equal(out[0][i][k], out[1][i][k], equal_nan=True), (N, prec, B, i, k)
+        s.close()
