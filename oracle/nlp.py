@@ -109,6 +109,20 @@ class Problem:
     obs: np.ndarray             # [N+1, 2] obstacle (x, y) forecast; row 0 unused (mpc.py:224)
     nn_ctx: tuple = None        # (s_tv, v_tv, e_tv, e_ego) for gt_mpc
     u_init: np.ndarray = None   # [N, 2] optional warm start (mpc.py:386-389)
+    obs_psi: np.ndarray = None  # [N+1] obstacle heading forecast: selects the OBCA collision rows (ca_type='obca',
+                                # mpc.py:211-221, d_min = 0) in their dual-eliminated form, see oracle/obca.py;
+                                # python oracle only so far (the C port and the CUDA solver implement 'circle')
+
+
+OBCA_MARGIN = 1e-6              # mpc.py:216: ... >= d_min + 1e-6 with d_min = 0 (mpc.py:42-43)
+
+
+def obca_rows(prob: Problem, Z):
+    """OBCA rows k = 1..N in eliminated form: margin - dist(ego rectangle_k, obstacle rectangle_k) <= 0."""
+    from . import obca
+    return np.array([OBCA_MARGIN - obca.rect_distance(Z[k, [D.IX, D.IY, D.IPSI]],
+                                                      np.array([prob.obs[k, 0], prob.obs[k, 1], prob.obs_psi[k]]))[0]
+                     for k in range(1, Z.shape[0])])
 
 
 def cost(P: Params, prob: Problem, Z, U, mlp: MLPTerm = None):
@@ -134,8 +148,11 @@ def inequality_rows(P: Params, prob: Problem, Z, U):
     rows += [-P.da_max - da, da - P.da_max, -P.ddf_max - ddf, ddf - P.ddf_max]
     rows += [ey - P.ey_lim, -P.ey_lim - ey]
     rows += [P.cinf_A @ np.array([v[N - 1], a[N - 1]]) - P.cinf_b]
-    dp = Z[1:, :2] - prob.obs[1:]
-    rows += [P.d_min ** 2 - np.sum(dp * dp, axis=1)]
+    if prob.obs_psi is not None:
+        rows += [obca_rows(prob, Z)]
+    else:
+        dp = Z[1:, :2] - prob.obs[1:]
+        rows += [P.d_min ** 2 - np.sum(dp * dp, axis=1)]
     return np.concatenate(rows)
 
 
@@ -190,8 +207,11 @@ def guess_merit(P: Params, prob: Problem, Z, U):
     v, ey = Z[:, D.IV], Z[:, D.IEY]
     viol = np.sum(np.maximum(0.0, v[1:N] - P.v_max)) + np.sum(np.maximum(0.0, P.v_min - v[1:N]))
     viol += np.sum(np.maximum(0.0, np.abs(ey[1:]) - P.ey_lim))
-    dist = np.sqrt(np.sum((Z[1:, :2] - prob.obs[1:]) ** 2, axis=1))
-    viol += np.sum(np.maximum(0.0, P.d_min - dist))
+    if prob.obs_psi is not None:
+        viol += np.sum(np.maximum(0.0, obca_rows(prob, Z)))
+    else:
+        dist = np.sqrt(np.sum((Z[1:, :2] - prob.obs[1:]) ** 2, axis=1))
+        viol += np.sum(np.maximum(0.0, P.d_min - dist))
     viol += np.sum(np.maximum(0.0, P.cinf_A @ np.array([v[N - 1], U[N - 1, 0]]) - P.cinf_b))
     return float(J + GUESS_RHO * viol)
 

@@ -32,7 +32,7 @@ def rotation_translation(x0, theta, h=VEH_LENGTH, w=VEH_WIDTH):
     return A, b
 
 
-def dual_value(ego, obs, h=VEH_LENGTH, w=VEH_WIDTH):
+def dual_value(ego, obs, h=VEH_LENGTH, w=VEH_WIDTH, return_arg=False):
     """max of -g' mu + (A p - b)' lambda over the reference's dual feasible set (mpc.py:216-221), by SLSQP from
     several starts.  ego, obs = (x, y, heading)."""
     A, b = rotation_translation(obs[:2], obs[2], h, w)
@@ -47,7 +47,7 @@ def dual_value(ego, obs, h=VEH_LENGTH, w=VEH_WIDTH):
 
     cons = [{'type': 'eq', 'fun': lambda v: G.T @ v[4:] + R.T @ A.T @ v[:4]},
             {'type': 'ineq', 'fun': lambda v: 1.0 - np.sum((A.T @ v[:4]) ** 2)}]
-    best = 0.0                                                                           # lambda = mu = 0 is feasible
+    best, arg = 0.0, np.zeros(8)                                                         # lambda = mu = 0 is feasible
     rng = np.random.default_rng(0)
     for _ in range(12):
         v0 = rng.uniform(0, 0.5, 8)
@@ -56,9 +56,9 @@ def dual_value(ego, obs, h=VEH_LENGTH, w=VEH_WIDTH):
         if res.success:
             v = res.x
             feas = np.max(np.abs(G.T @ v[4:] + R.T @ A.T @ v[:4])) < 1e-7 and np.sum((A.T @ v[:4]) ** 2) <= 1 + 1e-7
-            if feas:
-                best = max(best, -res.fun)
-    return best
+            if feas and -res.fun > best:
+                best, arg = -res.fun, v
+    return (best, arg) if return_arg else best
 
 
 def _corners(pose, h, w):
@@ -97,27 +97,58 @@ def _segments_cross(P, Q):
     return False
 
 
+def _penetration(ego, obs, h, w):
+    """Intersecting rectangles: minus the penetration depth (separating-axis test over the four face normals)
+    and its gradient w.r.t. the ego pose -- the continuation of the distance into the infeasible region, so that
+    an iterate that jumped into the obstacle sees how to get out (the clamped distance is flat there)."""
+    hl, hw = h / 2, w / 2
+    c, s = np.cos(ego[2]), np.sin(ego[2])
+    uxe, uye = np.array([c, s]), np.array([-s, c])
+    co, so = np.cos(obs[2]), np.sin(obs[2])
+    uxo, uyo = np.array([co, so]), np.array([-so, co])
+    dvec = np.asarray(ego[:2], dtype=float) - np.asarray(obs[:2], dtype=float)
+    sg = lambda v: 1.0 if v >= 0 else -1.0
+    best = None
+    for a, da, he in ((uxe, uye, hl), (uye, -uxe, hw)):           # ego face normals (turn with psi)
+        ho = hl * abs(a @ uxo) + hw * abs(a @ uyo)
+        ov = he + ho - abs(a @ dvec)
+        g_p = -sg(a @ dvec) * a
+        g_psi = hl * sg(a @ uxo) * (da @ uxo) + hw * sg(a @ uyo) * (da @ uyo) - sg(a @ dvec) * (da @ dvec)
+        if best is None or ov < best[0]:
+            best = (ov, g_p, g_psi)
+    for a, ho in ((uxo, hl), (uyo, hw)):                          # obstacle face normals (fixed)
+        he = hl * abs(a @ uxe) + hw * abs(a @ uye)
+        ov = he + ho - abs(a @ dvec)
+        g_p = -sg(a @ dvec) * a
+        g_psi = hl * sg(a @ uxe) * (a @ uye) + hw * sg(a @ uye) * (a @ -uxe)
+        if ov < best[0]:
+            best = (ov, g_p, g_psi)
+    ov, g_p, g_psi = best
+    return -ov, -np.array([g_p[0], g_p[1], g_psi])
+
+
 def rect_distance(ego, obs, h=VEH_LENGTH, w=VEH_WIDTH):
-    """Euclidean distance between the two rectangles (0 if they intersect) and its gradient with respect to the
-    ego pose (x, y, psi).  For disjoint convex polygons the minimum is attained between a vertex of one and the
-    boundary of the other, so the eight vertex-to-rectangle distances cover it."""
+    """Signed distance between the two rectangles -- the Euclidean distance if they are disjoint (which is what
+    the reference's dual rows certify), minus the penetration depth if they intersect -- and its gradient with
+    respect to the ego pose (x, y, psi).  For disjoint convex polygons the minimum is attained between a vertex of
+    one and the boundary of the other, so the eight vertex-to-rectangle distances cover it."""
     Pe, loc_e = _corners(ego, h, w)
     Po, _ = _corners(obs, h, w)
     best = (np.inf, None)
     for i in range(4):                                            # ego vertex -> obstacle rectangle
         d, cl_world, _, inside = _point_rect(Pe[i], obs, h, w)
         if inside:
-            return 0.0, np.zeros(3)
+            return _penetration(ego, obs, h, w)
         if d < best[0]:
             best = (d, ('ego_vertex', Pe[i], cl_world, loc_e[i]))
     for j in range(4):                                            # obstacle vertex -> ego rectangle
         d, cl_world, cl_local, inside = _point_rect(Po[j], ego, h, w)
         if inside:
-            return 0.0, np.zeros(3)
+            return _penetration(ego, obs, h, w)
         if d < best[0]:
             best = (d, ('obs_vertex', cl_world, Po[j], cl_local))
     if _segments_cross(Pe, Po):                                   # crossing edges without a vertex inside
-        return 0.0, np.zeros(3)
+        return _penetration(ego, obs, h, w)
     d, (_, a, bpt, a_local) = best
     n = (a - bpt) / d                                             # from the obstacle's closest point to the ego's
     c, s = np.cos(ego[2]), np.sin(ego[2])

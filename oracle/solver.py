@@ -83,8 +83,8 @@ def stage_rows(P, prob, k, z, up, u):
         add(P.v_min - z[D.IV], ex(D.IV, -1.0))               # mpc.py:316
         add(z[D.IEY] - P.ey_lim, ex(D.IEY))                  # mpc.py:298
         add(-P.ey_lim - z[D.IEY], ex(D.IEY, -1.0))           # mpc.py:299
-        cval, g, hc = collision_row(P, z, prob.obs[k])           # mpc.py:226 (distance form)
-        add(cval, g, None, hc)
+        cval, g, hc = collision_row(P, z, prob.obs[k], None if prob.obs_psi is None else prob.obs_psi[k])
+        add(cval, g, None, hc)                                   # mpc.py:226 (distance form) / :211-221 (OBCA)
     add(u[0] - P.a_max, None, eu(0))                          # mpc.py:319
     add(P.a_min - u[0], None, eu(0, -1.0))                    # mpc.py:318
     add(u[1] - P.df_max, None, eu(1))                         # mpc.py:321
@@ -102,10 +102,18 @@ def stage_rows(P, prob, k, z, up, u):
     return np.array(c), np.array(Cx), np.array(Cu), hxy
 
 
-def collision_row(P, z, o):
+def collision_row(P, z, o, o_psi=None):
     """mpc.py:226 writes d_min^2 - |p - o|^2 <= 0; the solvers use the equivalent, better scaled
     d_min - |p - o| <= 0 (same feasible set, multiplier scaled by 2|p - o|).  Returns the row
-    value, its gradient w.r.t. zeta and its 2x2 Hessian block on (x, y)."""
+    value, its gradient w.r.t. zeta and its 2x2 Hessian block on (x, y).
+    With an obstacle heading: the OBCA rows of mpc.py:211-221 with their duals maximised out
+    (oracle/obca.py): margin - rectangle distance, gradient on (x, y, psi), Gauss-Newton (no Hessian)."""
+    if o_psi is not None:
+        from . import obca
+        d, gd = obca.rect_distance(np.array([z[D.IX], z[D.IY], z[D.IPSI]]), np.array([o[0], o[1], o_psi]))
+        g = np.zeros(9)
+        g[D.IX], g[D.IY], g[D.IPSI] = -gd[0], -gd[1], -gd[2]
+        return nlp.OBCA_MARGIN - d, g, 0.0
     dx, dy = z[D.IX] - o[0], z[D.IY] - o[1]
     dist = max(np.hypot(dx, dy), 1e-9)
     nx_, ny_ = dx / dist, dy / dist
@@ -129,7 +137,7 @@ def terminal_rows(P, prob, z):
     c.append(z[D.IEY] - P.ey_lim); Cx.append(g); hxy.append(0.0)
     g = np.zeros(9); g[D.IEY] = -1.0
     c.append(-P.ey_lim - z[D.IEY]); Cx.append(g); hxy.append(0.0)
-    cval, g, hc = collision_row(P, z, prob.obs[N])
+    cval, g, hc = collision_row(P, z, prob.obs[N], None if prob.obs_psi is None else prob.obs_psi[N])
     c.append(cval); Cx.append(g); hxy.append(hc)
     return np.array(c), np.array(Cx), np.zeros((3, 2)), hxy
 

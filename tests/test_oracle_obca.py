@@ -29,20 +29,20 @@ def test_dual_formulation_equals_rectangle_distance():
     for ego, obs in _poses(rng, 40, 3.0, 12.0):
         d, _ = obca.rect_distance(ego, obs)
         v = obca.dual_value(ego, obs)
-        assert abs(d - v) < 1e-5 * max(1.0, d), (ego, obs, d, v)
+        assert abs(max(d, 0.0) - v) < 1e-5 * max(1.0, d), (ego, obs, d, v)      # the dual certifies distances, not depths
     # intersecting rectangles: the dual cannot certify any positive distance (lambda = mu = 0 is its optimum)
     for ego, obs in _poses(rng, 10, 0.0, 0.9):
         d, g = obca.rect_distance(ego, obs)
-        assert d == 0.0 and not g.any()
+        assert d <= 0.0                                            # minus the penetration depth
         assert obca.dual_value(ego, obs) < 1e-6
 
 
 def test_rectangle_distance_gradient():
     rng = np.random.default_rng(3)
     checked = 0
-    for ego, obs in _poses(rng, 60, 3.5, 10.0):
+    for ego, obs in _poses(rng, 60, 3.5, 10.0) + _poses(rng, 30, 0.2, 1.5):      # disjoint and intersecting
         d, g = obca.rect_distance(ego, obs)
-        if d < 0.05:
+        if abs(d) < 0.05:
             continue
         fd = np.zeros(3)
         smooth = True
@@ -55,7 +55,81 @@ def test_rectangle_distance_gradient():
         if smooth:
             assert np.allclose(g, fd, atol=2e-5), (ego, obs, g, fd)
             checked += 1
-    assert checked >= 40
+    assert checked >= 55
     # a hand-checkable case: two axis-aligned cars 7 m apart nose to tail: distance 7 - 4.47, gradient (+-1, 0, 0)
     d, g = obca.rect_distance(np.array([7.0, 0.0, 0.0]), np.array([0.0, 0.0, 0.0]))
     assert abs(d - (7.0 - 4.47)) < 1e-12 and np.allclose(g[:2], [1.0, 0.0])
+
+
+def test_obca_mpc_eliminated_rows_vs_reference_formulation_with_explicit_duals():
+    """A small MPC problem in OBCA mode, solved (a) by the python oracle with the ONE eliminated row per stage and
+    (b) by scipy SLSQP on the reference's own formulation -- lambda_k, mu_k in R^4 as decision variables with the
+    rows of mpc.py:216-221: the same optimum, with the collision row active."""
+    from scipy.optimize import minimize
+    from oracle import nlp, solver, dynamics as D
+    N = 8
+    base = nlp.Params(N=40)
+    P = nlp.Params(N=N, cinf_A=base.cinf_A, cinf_b=base.cinf_b)
+    x0 = np.array([5.0, 2.8, 5.0, 0.0, 0.0, 3.0, 0.0])
+    opose = np.array([11.4, 3.6, 1.1])                             # a car standing askew across the ego's lane: the
+                                                                   # ego slows down and swerves to the lane's edge
+    prob = nlp.Problem(x0=x0, u_prev=np.array([0.0, 0.0]), curv=(1e30, 1e30, 0.0),
+                       obs=np.tile(opose[:2], (N + 1, 1)), obs_psi=np.full(N + 1, opose[2]))
+    r = solver.solve(P, prob)
+    assert r.status == 0 and r.viol <= 1e-9
+    d_end = obca.rect_distance(r.Z[N, [0, 1, 6]], opose)[0]
+    assert abs(d_end - nlp.OBCA_MARGIN) < 1e-7                       # the row is active at the end of the horizon
+    free = solver.solve(P, nlp.Problem(x0=x0, u_prev=prob.u_prev, curv=prob.curv, obs=np.full((N + 1, 2), -50.0)))
+    assert free.cost < r.cost - 1e-3                               # and it costs progress
+
+    # (b) the reference's formulation: variables u[N,2], lambda[N,4], mu[N,4] (k = 1..N), single shooting for x
+    G, g = obca.rotation_translation([0.0, 0.0], 0.0)
+    A, b = obca.rotation_translation(opose[:2], opose[2])
+    other = nlp.Problem(x0=x0, u_prev=prob.u_prev, curv=prob.curv, obs=np.full((N + 1, 2), -50.0))   # rows without collision
+
+    def unpack(v):
+        return v[:2 * N].reshape(N, 2), v[2 * N:6 * N].reshape(N, 4), v[6 * N:].reshape(N, 4)
+
+    def roll(U):
+        return D.frenet_rollout(x0, U, prob.curv, P.dt, P.n_rk)
+
+    def f(v):
+        U = unpack(v)[0]
+        return nlp.cost(P, other, roll(U), U)
+
+    def ineq(v):
+        U, lam, mu = unpack(v)
+        Z = roll(U)
+        rows = [-nlp.inequality_rows(P, other, Z, U)]
+        for k in range(1, N + 1):
+            p = Z[k, :2]
+            rows.append([-g @ mu[k - 1] + (A @ p - b) @ lam[k - 1] - nlp.OBCA_MARGIN,          # mpc.py:216
+                         1.0 - np.sum((A.T @ lam[k - 1]) ** 2)])                                # mpc.py:218
+        return np.concatenate([np.ravel(x) for x in rows])
+
+    def eq(v):
+        U, lam, mu = unpack(v)
+        Z = roll(U)
+        out = []
+        for k in range(1, N + 1):
+            c, s = np.cos(Z[k, 6]), np.sin(Z[k, 6])
+            R = np.array([[c, -s], [s, c]])
+            out.append(G.T @ mu[k - 1] + R.T @ A.T @ lam[k - 1])                               # mpc.py:217
+        return np.concatenate(out)
+
+    # started next to the oracle's solution (controls perturbed by 0.02, duals at their per-stage optimum): the
+    # bilinear dual formulation is too degenerate for SLSQP from a cold start, but it must come back to the same point
+    rng = np.random.default_rng(1)
+    U0 = r.U + 0.02 * rng.normal(size=r.U.shape)
+    duals = [obca.dual_value(r.Z[k, [0, 1, 6]], opose, return_arg=True)[1] for k in range(1, N + 1)]
+    v_star = np.concatenate([r.U.ravel(), np.array([d[:4] for d in duals]).ravel(), np.array([d[4:] for d in duals]).ravel()])
+    assert ineq(v_star).min() > -1e-9 and np.abs(eq(v_star)).max() < 1e-9      # the oracle's point is feasible for the reference's rows
+    v0 = v_star.copy(); v0[:2 * N] = U0.ravel()
+    bounds = [(None, None)] * (2 * N) + [(0, None)] * (8 * N)
+    res = minimize(f, v0, method="SLSQP", bounds=bounds,
+                   constraints=[{"type": "ineq", "fun": ineq}, {"type": "eq", "fun": eq}],
+                   options={"maxiter": 300, "ftol": 1e-10})
+    assert res.success, res.message
+    U = unpack(res.x)[0]
+    assert abs(res.fun - r.cost) < 1e-5 * max(1.0, abs(r.cost)), (res.fun, r.cost)
+    assert np.max(np.abs(U - r.U)) < 2e-3
