@@ -103,7 +103,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons}
 
 
-def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0, max_trials=0):
+def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0, max_trials=0, ctx=None):
     """The oracle's C restatement timed on the host cores on the first n_sample problems."""
     from oracle import nlp, c_oracle
     P = nlp.Params(N=N)
@@ -111,9 +111,10 @@ def cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, max_iter, threads=0, ma
     if mode == "gt_mpc":
         term = nlp.MLPTerm(weights=mlp["weights"], Wn=mlp["Wn"], mu_f=mlp["mu_f"], sigma_t=mlp["sigma_t"], mu_t=mlp["mu_t"])
     co = c_oracle.COracle(P, term, max_iter=max_iter, max_trials=max_trials)
-    co.solve(x0[:64], up[:64], cv[:64], ob[:64], n_threads=threads)           # warm the library / page in
+    c_of = lambda n: None if term is None else ctx[:n]
+    co.solve(x0[:64], up[:64], cv[:64], ob[:64], nn_ctx=c_of(64), n_threads=threads)           # warm the library / page in
     t0 = time.perf_counter()
-    r = co.solve(x0[:n_sample], up[:n_sample], cv[:n_sample], ob[:n_sample], n_threads=threads)
+    r = co.solve(x0[:n_sample], up[:n_sample], cv[:n_sample], ob[:n_sample], nn_ctx=c_of(n_sample), n_threads=threads)
     dt = time.perf_counter() - t0
     return int((r["status"] == 0).sum()), dt
 
@@ -127,10 +128,10 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     n_sample = min(len(x0), max(256, 64 * cores))
     for _ in range(args.warmup):
-        cpu_baseline(x0, up, cv, ob, N, mode, mlp, min(256, n_sample), MAX_ITER_DEFAULT)
+        cpu_baseline(x0, up, cv, ob, N, mode, mlp, min(256, n_sample), MAX_ITER_DEFAULT, ctx=ctx)
     conv, tsum = 0, 0.0
     for _ in range(args.steps):
-        c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, MAX_ITER_DEFAULT)
+        c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, MAX_ITER_DEFAULT, ctx=ctx)
         conv += c
         tsum += dt
     val = conv / tsum
@@ -332,7 +333,7 @@ def main():
             cores = os.cpu_count() or 1
             n_sample = min(B, max(512, 128 * cores))
             c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, solver.params.max_iter,
-                                 max_trials=solver.params.max_trials)
+                                 max_trials=solver.params.max_trials, ctx=ctx)
             line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "first %d problems of the same batch, oracle fp64 C restatement on all "
                                               "host threads (the reference's CasADi/IPOPT solver is not installable "

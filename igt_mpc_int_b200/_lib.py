@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("IGT_LIB", os.path.join(_HERE, "lib", "libigtmpc.so"))
 MAX_CINF, MAX_LAYERS = 128, 5
 PREC_F32, PREC_F64 = 0, 1
 STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "x0_infeasible", 3: "reg_limit", 4: "line_search",
-                5: "stalled_infeasible"}
+                5: "stalled_infeasible", 6: "acceptable"}
+STATUS_OK = (0, 6)      # converged, or stopped within the reference's own IPOPT tolerances (igt_mpc.h: IGT_STATUS_ACCEPTABLE)
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -42,6 +43,7 @@ class IgtParams(C.Structure):
         ("eps_phi", C.c_double), ("gamma_theta", C.c_double), ("theta_small", C.c_double),
         ("max_iter", C.c_int), ("n_alpha", C.c_int), ("second_order", C.c_int),
         ("stall_iter", C.c_int), ("stall_rp", C.c_double), ("max_trials", C.c_int), ("precision", C.c_int),
+        ("acc_tol", C.c_double), ("acc_rp", C.c_double), ("acc_comp", C.c_double), ("x0_tol", C.c_double),
     ]
 
     def set_cinf(self, A, b):
@@ -86,9 +88,9 @@ def load():
     lib.igt_set_mlp.argtypes = [vp, C.c_int, _ip, C.POINTER(_dp), C.POINTER(_dp), _dp, _dp, C.c_double, C.c_double]
     lib.igt_rollout_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp]
     lib.igt_rollout_host.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
-    lib.igt_eval_host.argtypes = [vp, C.c_int] + [vp] * 9
-    lib.igt_solve_dev.argtypes = [vp, C.c_int] + [vp] * 12 + [vp]
-    lib.igt_solve_host.argtypes = [vp, C.c_int] + [vp] * 12
+    lib.igt_eval_host.argtypes = [vp, C.c_int] + [vp] * 10
+    lib.igt_solve_dev.argtypes = [vp, C.c_int] + [vp] * 13 + [vp]
+    lib.igt_solve_host.argtypes = [vp, C.c_int] + [vp] * 13
     lib.igt_launch_count.argtypes = [vp]
     lib.igt_measure_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.igt_measure_fma_peak.restype = C.c_int

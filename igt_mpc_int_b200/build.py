@@ -8,7 +8,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(_HERE, "csrc", f) for f in ("igt_abi.cu",)]
-DEPS = SRC + [os.path.join(_HERE, "csrc", f) for f in ("solver_core.cuh", "params_host.hpp", "mlp_tc.cuh")] + \
+DEPS = SRC + [os.path.join(_HERE, "csrc", f) for f in ("solver_core.cuh", "params_host.hpp", "mlp_tc.cuh", "obca.cuh")] + \
        [os.path.join(_HERE, "..", "include", "igt_mpc.h")]
 OUT = os.path.join(_HERE, "lib", "libigtmpc.so")
 

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <mutex>
 
 #include "../../include/igt_mpc.h"
 #include "solver_core.cuh"
@@ -29,36 +30,42 @@ using namespace igt;
 #define SLOTS_PER_SM SOLVE_BLOCK
 
 // ------------------------------------------------------------------ device constants ----
-__constant__ DevParams<float> c_Pf;
-__constant__ DevParams<double> c_Pd;
+// Solver parameters live in constant memory, N_CSLOTS copies per precision: every handle owns a slot (handles
+// beyond N_CSLOTS per device share one, ordered by events -- see acquire_cslot), kernels get the slot index as an
+// argument, and a slot is uploaded only when its content changes.  Handles with different horizons, limits or value
+// networks can therefore run concurrently on different streams.
+constexpr int N_CSLOTS = 8;
+__constant__ DevParams<float> c_Pf[N_CSLOTS];
+__constant__ DevParams<double> c_Pd[N_CSLOTS];
+static_assert(N_CSLOTS * (sizeof(DevParams<float>) + sizeof(DevParams<double>)) <= 60 * 1024, "constant memory budget");
 
-template <> struct igt::ConstP<float> { static __device__ __forceinline__ const DevParams<float> &get() { return c_Pf; } };
-template <> struct igt::ConstP<double> { static __device__ __forceinline__ const DevParams<double> &get() { return c_Pd; } };
+template <> struct igt::ConstP<float> { static __device__ __forceinline__ const DevParams<float> &get(int s) { return c_Pf[s]; } };
+template <> struct igt::ConstP<double> { static __device__ __forceinline__ const DevParams<double> &get(int s) { return c_Pd[s]; } };
 
 // ------------------------------------------------------------------ kernels -------------
 // cold-start guess: best of five tracking-controller rollouts per problem -> guess[B][N][2]
-template <typename T>
-__global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *guess)
+template <typename T, bool OBCA>
+__global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *guess, int cs)
 {
     long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
-    const DevParams<T> &P = ConstP<T>::get();
-    Solver<T> sv(P);
+    const DevParams<T> &P = ConstP<T>::get(cs);
+    Solver<T, Ws<T, 32, OBCA>> sv(P);
     sv.compute_guess(io, p, guess + p * P.N * 2);
 }
 
-template <typename T, bool TC>
+template <typename T, bool TC, bool OBCA>
 __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws, long n_slots, long B, Sched sc,
                                                                const double *guess, T *mlp_scratch, int mlp_width,
-                                                               MlpTcWeights wt, int quota)
+                                                               MlpTcWeights wt, int quota, int cs)
 {
     extern __shared__ uint8_t dyn_smem[];
     long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;   // grid is sized to n_slots exactly
-    const DevParams<T> &P = ConstP<T>::get();
+    const DevParams<T> &P = ConstP<T>::get(cs);
     MlpTcCtx tc;
     if (TC) mlp_tc_setup(tc, dyn_smem, wt);
-    solve_persistent<T, TC>(P, io, ws, slot, B, sc, guess,
-                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc, quota);
+    solve_persistent<T, TC, 32, OBCA>(P, io, ws, slot, B, sc, guess,
+                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc, quota, cs);
     if (TC) mlp_tc_teardown(tc);
 }
 
@@ -66,12 +73,12 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws,
 // its whole workspace in shared memory (stride-1 layout), so the sweeps of the problem's one owner thread run at
 // shared-memory latency instead of an L2 round trip per stage; the node phases and the line-search candidates
 // are dealt out over the CTA's 256 threads as in the throughput kernel.  Same code, same arithmetic, same results.
-template <typename T>
-__global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_small_kernel(ProbIO io, long B, Sched sc, const double *guess)
+template <typename T, bool OBCA>
+__global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_small_kernel(ProbIO io, long B, Sched sc, const double *guess, int cs)
 {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    const DevParams<T> &P = ConstP<T>::get();
-    solve_persistent<T, false, 1>(P, io, reinterpret_cast<T *>(dyn_smem), 0, B, sc, guess, (T *)nullptr, 0, nullptr, 1);
+    const DevParams<T> &P = ConstP<T>::get(cs);
+    solve_persistent<T, false, 1, OBCA>(P, io, reinterpret_cast<T *>(dyn_smem), 0, B, sc, guess, (T *)nullptr, 0, nullptr, 1, cs);
 }
 
 // fp32 rollout with Kahan-compensated accumulation of the RK4 increments (x, y, s reach ~50 m
@@ -80,11 +87,11 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_small_kernel(ProbIO io, 
 __global__ void __launch_bounds__(128) rollout_kernel(int B, const float *__restrict__ z0,
                                                       const float *__restrict__ U,
                                                       const float *__restrict__ curv_, float *__restrict__ Z,
-                                                      float *__restrict__ A, float *__restrict__ Bm)
+                                                      float *__restrict__ A, float *__restrict__ Bm, int cs)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
-    const DevParams<float> &P = c_Pf;
+    const DevParams<float> &P = c_Pf[cs];
     const int N = P.N;
     float z[NZ], comp[NZ], curv[3] = { curv_[3 * p], curv_[3 * p + 1], curv_[3 * p + 2] };
 #pragma unroll
@@ -141,11 +148,11 @@ __global__ void __launch_bounds__(128) rollout_kernel(int B, const float *__rest
 
 __global__ void __launch_bounds__(128) rollout_euler_kernel(int B, const float *__restrict__ z0,
                                                             const float *__restrict__ U, float *__restrict__ Z,
-                                                            float *__restrict__ A, float *__restrict__ Bm)
+                                                            float *__restrict__ A, float *__restrict__ Bm, int cs)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
-    const DevParams<float> &P = c_Pf;
+    const DevParams<float> &P = c_Pf[cs];
     const int N = P.N;
     float z[4];
     for (int i = 0; i < 4; i++) { z[i] = z0[(long)p * 4 + i]; Z[(long)p * (N + 1) * 4 + i] = z[i]; }
@@ -161,11 +168,12 @@ __global__ void __launch_bounds__(128) eval_kernel(long B, const double *__restr
                                                    const double *__restrict__ curv_, const double *__restrict__ obs_,
                                                    const double *__restrict__ ctx_, const double *__restrict__ U,
                                                    double *__restrict__ cost, double *__restrict__ viol,
-                                                   double *__restrict__ Zout, double *mlp_scratch, int mlp_width)
+                                                   double *__restrict__ Zout, double *mlp_scratch, int mlp_width, int cs,
+                                                   const double *__restrict__ obs_psi_)
 {
     long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
-    const DevParams<double> &P = c_Pd;
+    const DevParams<double> &P = c_Pd[cs];
     const int N = P.N;
     double z[NZ], curv[3] = { curv_[3 * p], curv_[3 * p + 1], curv_[3 * p + 2] };
     double up[2] = { uprev_[2 * p], uprev_[2 * p + 1] };
@@ -177,8 +185,13 @@ __global__ void __launch_bounds__(128) eval_kernel(long B, const double *__restr
         J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
         m = fmax(m, fabs(z[IEY]) - P.ey_lim);
         if (k >= 1) {
-            double dx = z[IX] - obs[2 * k], dy = z[IY] - obs[2 * k + 1];
-            m = fmax(m, P.d_min * P.d_min - dx * dx - dy * dy);
+            if (obs_psi_) {                                      // OBCA rows in dual-eliminated form (obca.cuh)
+                double gd[3];
+                m = fmax(m, P.d_min + OBCA_MARGIN - obca_rect_sdist(z[IX], z[IY], z[IPSI], obs[2 * k], obs[2 * k + 1], obs_psi_[p * (N + 1) + k], gd));
+            } else {
+                double dx = z[IX] - obs[2 * k], dy = z[IY] - obs[2 * k + 1];
+                m = fmax(m, P.d_min * P.d_min - dx * dx - dy * dy);
+            }
         }
         if (k == N) break;
         double u[2] = { U[(p * N + k) * 2], U[(p * N + k) * 2 + 1] };
@@ -230,11 +243,11 @@ __global__ void __launch_bounds__(256, 1) mlp_tc_kernel(MlpTcWeights wt, long B,
 }
 
 __global__ void __launch_bounds__(128) mlp_ref_kernel(long B, const double *sN, const double *vN, const double *ctx,
-                                                      double *out, double *scratch, int width)
+                                                      double *out, double *scratch, int width, int cs)
 {
     long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
-    const DevParams<double> &P = c_Pd;
+    const DevParams<double> &P = c_Pd[cs];
     TermVal<double> t;
     double cx[4] = { ctx[4 * p], ctx[4 * p + 1], ctx[4 * p + 2], ctx[4 * p + 3] };
     double *sc = scratch + p * 12 * (long)width;
@@ -275,7 +288,24 @@ struct igt_handle {
     long long launches = 0;
     std::string err;
     int device = 0;
+    // concurrency (see the header): calls on one handle are serialised on the device in call order whatever their
+    // streams -- the handle's workspace, guess buffer and work counter are shared by its calls
+    std::mutex mu;                     // host-side: one call at a time per handle
+    cudaStream_t hstream = nullptr;    // the *_host entry points run on a private non-blocking stream
+    void *pin = nullptr; size_t pin_bytes = 0;   // pinned staging block of igt_solve_host (small batches)
+    cudaEvent_t last_use = nullptr;    // recorded after the last kernel of every call
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
+    unsigned long long version[2] = { 1, 1 };   // bumped when Pf / Pd change (igt_set_mlp)
+    int cslot[2] = { -1, -1 };
 };
+
+// constant-memory slot table, per device and precision (0 = f32, 1 = f64)
+struct CSlot { const igt_handle *owner = nullptr; unsigned long long version = 0; cudaEvent_t ev = nullptr; };
+constexpr int MAX_DEV = 16;
+static std::mutex g_slot_mu;
+static CSlot g_slots[MAX_DEV][2][N_CSLOTS];
+static unsigned g_slot_rr[MAX_DEV][2];
 
 static std::string g_create_err;
 
@@ -288,12 +318,65 @@ static std::string g_create_err;
         }                                                                                          \
     } while (0)
 
-static int grow(igt_handle *h, void **buf, size_t *have, size_t need)
+// (re)allocation is stream-ordered: the old buffer is released after the work already queued on `st` (which, by
+// begin_call, includes every earlier call on this handle), the new one is usable by work queued on `st` afterwards
+static int grow(igt_handle *h, void **buf, size_t *have, size_t need, cudaStream_t st)
 {
     if (*have >= need) return IGT_OK;
-    if (*buf) { CK(cudaFree(*buf)); *buf = nullptr; *have = 0; }
-    CK(cudaMalloc(buf, need));
+    if (*buf) { CK(cudaFreeAsync(*buf, st)); *buf = nullptr; *have = 0; }
+    CK(cudaMallocAsync(buf, need, st));
     *have = need;
+    return IGT_OK;
+}
+
+// Entry of every call that queues device work for a handle: select its device and order the call after the
+// handle's previous call if that one went to a different stream.
+static int begin_call(igt_handle *h, cudaStream_t st)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->last_use) CK(cudaEventCreateWithFlags(&h->last_use, cudaEventDisableTiming));
+    if (h->used && h->last_stream != st) CK(cudaStreamWaitEvent(st, h->last_use, 0));
+    return IGT_OK;
+}
+
+// Constant-memory slot holding this handle's parameters in `prec` (0 = f32, 1 = f64), uploaded if it does not
+// hold them yet.  A slot taken over from another handle is first made to wait for that handle's kernels.
+static int acquire_cslot(igt_handle *h, int prec, cudaStream_t st, int *slot_out)
+{
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    const int dev = h->device < MAX_DEV ? h->device : MAX_DEV - 1;
+    CSlot *tab = g_slots[dev][prec];
+    int sl = h->cslot[prec];
+    if (sl < 0 || tab[sl].owner != h) {
+        sl = -1;
+        for (int i = 0; i < N_CSLOTS && sl < 0; i++) if (!tab[i].owner) sl = i;
+        if (sl < 0) sl = (int)(g_slot_rr[dev][prec]++ % N_CSLOTS);       // all taken: share, ordered by the slot's event
+        h->cslot[prec] = sl;
+    }
+    CSlot &c = tab[sl];
+    if (c.owner != h || c.version != h->version[prec]) {
+        if (c.ev) CK(cudaStreamWaitEvent(st, c.ev, 0));                    // kernels still reading the old content
+        if (prec) CK(cudaMemcpyToSymbolAsync(c_Pd, &h->Pd, sizeof(h->Pd), (size_t)sl * sizeof(h->Pd), cudaMemcpyHostToDevice, st));
+        else CK(cudaMemcpyToSymbolAsync(c_Pf, &h->Pf, sizeof(h->Pf), (size_t)sl * sizeof(h->Pf), cudaMemcpyHostToDevice, st));
+        c.owner = h; c.version = h->version[prec];
+    }
+    *slot_out = sl;
+    return IGT_OK;
+}
+
+// Exit of every such call: later users of the handle / of its constant slots wait for these events.
+static int end_call(igt_handle *h, cudaStream_t st, int prec_used_mask)
+{
+    CK(cudaEventRecord(h->last_use, st));
+    h->last_stream = st; h->used = true;
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    const int dev = h->device < MAX_DEV ? h->device : MAX_DEV - 1;
+    for (int prec = 0; prec < 2; prec++)
+        if ((prec_used_mask >> prec) & 1) {
+            CSlot &c = g_slots[dev][prec][h->cslot[prec]];
+            if (!c.ev) CK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+            CK(cudaEventRecord(c.ev, st));
+        }
     return IGT_OK;
 }
 
@@ -332,7 +415,18 @@ int igt_create(const igt_params *p, igt_handle **out)
 void igt_destroy(igt_handle *h)
 {
     if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->last_use) { cudaEventSynchronize(h->last_use); cudaEventDestroy(h->last_use); }
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        const int dev = h->device < MAX_DEV ? h->device : MAX_DEV - 1;
+        for (int prec = 0; prec < 2; prec++)
+            for (int i = 0; i < N_CSLOTS; i++)
+                if (g_slots[dev][prec][i].owner == h) { g_slots[dev][prec][i].owner = nullptr; g_slots[dev][prec][i].version = 0; }
+    }
     for (void *b : h->mlp_bufs) cudaFree(b);
+    if (h->hstream) cudaStreamDestroy(h->hstream);
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->ws) cudaFree(h->ws);
     if (h->mlp_scratch) cudaFree(h->mlp_scratch);
     if (h->stage) cudaFree(h->stage);
@@ -350,6 +444,10 @@ int igt_set_mlp(igt_handle *h, int n_layers, const int *dims, const double *cons
     if (!h) return IGT_EINVAL;
     if (n_layers < 1 || n_layers > IGT_MAX_MLP_LAYERS || !dims || !W || !b || !Wn || !mu_f || dims[0] != 6 ||
         dims[n_layers] != 1) { h->err = "igt_set_mlp: bad layer description"; return IGT_EINVAL; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (h->last_use && h->used) CK(cudaEventSynchronize(h->last_use));   // no kernel of this handle reads the old network
+    h->version[0]++; h->version[1]++;
     for (void *q : h->mlp_bufs) cudaFree(q);
     h->mlp_bufs.clear();
     int width = 6;
@@ -423,29 +521,30 @@ int igt_set_mlp(igt_handle *h, int n_layers, const int *dims, const double *cons
     return IGT_OK;
 }
 
-static int upload_params(igt_handle *h, cudaStream_t st, bool f32, bool f64)
+static int rollout_dev_impl(igt_handle *h, int B, const float *z0, const float *u, const float *curv, float *z,
+                            float *A, float *Bm, int model, cudaStream_t st)
 {
-    if (f32) CK(cudaMemcpyToSymbolAsync(c_Pf, &h->Pf, sizeof(h->Pf), 0, cudaMemcpyHostToDevice, st));
-    if (f64) CK(cudaMemcpyToSymbolAsync(c_Pd, &h->Pd, sizeof(h->Pd), 0, cudaMemcpyHostToDevice, st));
-    return IGT_OK;
+    if (B < 0 || !z0 || !u || !z || (model == 0 && !curv) || ((A == nullptr) != (Bm == nullptr)) ||
+        (model != 0 && model != 1)) { h->err = "igt_rollout: bad argument"; return IGT_EINVAL; }
+    if (B == 0) return IGT_OK;
+    int rc = begin_call(h, st), cs = 0;
+    if (rc) return rc;
+    rc = acquire_cslot(h, 0, st, &cs);
+    if (rc) return rc;
+    int bs = 128, gs = (B + bs - 1) / bs;
+    if (model == 0) rollout_kernel<<<gs, bs, 0, st>>>(B, z0, u, curv, z, A, Bm, cs);
+    else rollout_euler_kernel<<<gs, bs, 0, st>>>(B, z0, u, z, A, Bm, cs);
+    h->launches++;
+    CK(cudaGetLastError());
+    return end_call(h, st, 1);
 }
 
 int igt_rollout_dev(igt_handle *h, int B, const float *z0, const float *u, const float *curv, float *z,
                     float *A, float *Bm, int model, void *stream)
 {
     if (!h) return IGT_EINVAL;
-    if (B < 0 || !z0 || !u || !z || (model == 0 && !curv) || ((A == nullptr) != (Bm == nullptr)) ||
-        (model != 0 && model != 1)) { h->err = "igt_rollout: bad argument"; return IGT_EINVAL; }
-    if (B == 0) return IGT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc = upload_params(h, st, true, false);
-    if (rc) return rc;
-    int bs = 128, gs = (B + bs - 1) / bs;
-    if (model == 0) rollout_kernel<<<gs, bs, 0, st>>>(B, z0, u, curv, z, A, Bm);
-    else rollout_euler_kernel<<<gs, bs, 0, st>>>(B, z0, u, z, A, Bm);
-    h->launches++;
-    CK(cudaGetLastError());
-    return IGT_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return rollout_dev_impl(h, B, z0, u, curv, z, A, Bm, model, (cudaStream_t)stream);
 }
 
 int igt_rollout_host(igt_handle *h, int B, const float *z0, const float *u, const float *curv, float *z,
@@ -454,37 +553,40 @@ int igt_rollout_host(igt_handle *h, int B, const float *z0, const float *u, cons
     if (!h) return IGT_EINVAL;
     if (B < 0 || !z0 || !u || !z || (model == 0 && !curv)) { h->err = "igt_rollout: bad argument"; return IGT_EINVAL; }
     if (B == 0) return IGT_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    { int rc0 = begin_call(h, nullptr); if (rc0) return rc0; }
     const int N = h->prm.N, nz = model == 0 ? 7 : 4;
     size_t n_z0 = (size_t)B * nz, n_u = (size_t)B * N * 2, n_c = (size_t)B * 3, n_z = (size_t)B * (N + 1) * nz;
     size_t n_A = A ? (size_t)B * N * nz * nz : 0, n_B = A ? (size_t)B * N * nz * 2 : 0;
     size_t total = (n_z0 + n_u + n_c + n_z + n_A + n_B) * sizeof(float);
-    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    int rc = grow(h, &h->stage, &h->stage_bytes, total, nullptr);
     if (rc) return rc;
     float *d = (float *)h->stage;
     float *dz0 = d, *du = dz0 + n_z0, *dc = du + n_u, *dz = dc + n_c, *dA = dz + n_z, *dB = dA + n_A;
     CK(cudaMemcpy(dz0, z0, n_z0 * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(du, u, n_u * 4, cudaMemcpyHostToDevice));
     if (model == 0) CK(cudaMemcpy(dc, curv, n_c * 4, cudaMemcpyHostToDevice));
-    rc = igt_rollout_dev(h, B, dz0, du, dc, dz, A ? dA : nullptr, A ? dB : nullptr, model, nullptr);
+    rc = rollout_dev_impl(h, B, dz0, du, dc, dz, A ? dA : nullptr, A ? dB : nullptr, model, nullptr);
     if (rc) return rc;
     CK(cudaMemcpy(z, dz, n_z * 4, cudaMemcpyDeviceToHost));
     if (A) { CK(cudaMemcpy(A, dA, n_A * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(Bm, dB, n_B * 4, cudaMemcpyDeviceToHost)); }
     return IGT_OK;
 }
 
-int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
-                  const double *obs_xy, const double *nn_ctx, const double *u_init, double *x, double *u,
-                  double *cost, double *viol, int *status, int *iters, void *stream)
+static int solve_dev_impl(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                          const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u_init,
+                          double *x, double *u, double *cost, double *viol, int *status, int *iters, cudaStream_t st)
 {
-    if (!h) return IGT_EINVAL;
     if (B < 0 || !x0 || !u_prev || !curv || !obs_xy || !x || !u || !cost || !viol || !status || !iters) {
         h->err = "igt_solve: null argument"; return IGT_EINVAL;
     }
     if (nn_ctx && !h->has_mlp) { h->err = "igt_solve: nn_ctx given but igt_set_mlp was never called"; return IGT_ENOMLP; }
+    const bool f64 = h->prm.precision == IGT_PREC_F64, obca = obs_psi != nullptr;
+    if (obca && !f64) { h->err = "igt_solve: the OBCA collision rows (obs_psi) need precision f64"; return IGT_EINVAL; }
     if (B == 0) return IGT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool f64 = h->prm.precision == IGT_PREC_F64;
-    WsLayout L; L.init(h->prm.N, h->prm.n_cinf);
+    int rc = begin_call(h, st), cs = 0;
+    if (rc) return rc;
+    WsLayout L; L.init(h->prm.N, h->prm.n_cinf, obca ? NGE_OBCA : NGE, obca ? NHE_OBCA : NHE);
     size_t esz = f64 ? 8 : 4;
     // latency path: at most one problem per SM and a workspace that fits shared memory next to the work lists
     const size_t small_smem = (size_t)L.total * esz;
@@ -499,133 +601,197 @@ int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, 
     int quota = (int)((per_cta + 31) / 32 * 32);
     if (quota > bs) quota = bs;
     long n_slots = n_cta * bs;
-    int rc = small ? IGT_OK : grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * n_slots * esz);
+    rc = small ? IGT_OK : grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * n_slots * esz, st);
     if (rc) return rc;
     if (nn_ctx) {
-        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * n_slots * esz);
+        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * n_slots * esz, st);
         if (rc) return rc;
     }
     // scheduler block (the work counter), then the cold-start guesses
     const size_t off_guess = 256;
-    rc = grow(h, &h->guess, &h->guess_bytes, off_guess + (size_t)B * h->prm.N * 2 * sizeof(double));
+    rc = grow(h, &h->guess, &h->guess_bytes, off_guess + (size_t)B * h->prm.N * 2 * sizeof(double), st);
     if (rc) return rc;
     char *sb = (char *)h->guess;
     Sched sc;
     sc.counter = (unsigned long long *)sb;
     double *guess = (double *)(sb + off_guess);
-    rc = upload_params(h, st, !f64, f64);
+    rc = acquire_cslot(h, f64 ? 1 : 0, st, &cs);
     if (rc) return rc;
     CK(cudaMemsetAsync(sb, 0, 256, st));
     ProbIO io = { x0, u_prev, curv, obs_xy, nn_ctx, u_init, x, u, cost, viol, status, iters };
+    io.obs_psi = obs_psi;
     if (!u_init) {
         int gbs = 128, ggs = (B + gbs - 1) / gbs;
-        if (f64) guess_kernel<double><<<ggs, gbs, 0, st>>>(io, B, guess);
-        else guess_kernel<float><<<ggs, gbs, 0, st>>>(io, B, guess);
+        if (obca) guess_kernel<double, true><<<ggs, gbs, 0, st>>>(io, B, guess, cs);
+        else if (f64) guess_kernel<double, false><<<ggs, gbs, 0, st>>>(io, B, guess, cs);
+        else guess_kernel<float, false><<<ggs, gbs, 0, st>>>(io, B, guess, cs);
         h->launches++;
     }
     int gs = (int)(n_slots / bs);
-    const bool use_tc = nn_ctx && h->tc.enabled && h->use_tc;
+    const bool use_tc = nn_ctx && h->tc.enabled && h->use_tc && !obca;   // (OBCA + gt_mpc: CUDA-core value term)
     if (small) {
-        if (f64) {
-            CK(cudaFuncSetAttribute(solve_small_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
-            solve_small_kernel<double><<<B, bs, small_smem, st>>>(io, B, sc, guess);
+        if (obca) {
+            CK(cudaFuncSetAttribute(solve_small_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+            solve_small_kernel<double, true><<<B, bs, small_smem, st>>>(io, B, sc, guess, cs);
+        } else if (f64) {
+            CK(cudaFuncSetAttribute(solve_small_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+            solve_small_kernel<double, false><<<B, bs, small_smem, st>>>(io, B, sc, guess, cs);
         } else {
-            CK(cudaFuncSetAttribute(solve_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
-            solve_small_kernel<float><<<B, bs, small_smem, st>>>(io, B, sc, guess);
+            CK(cudaFuncSetAttribute(solve_small_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+            solve_small_kernel<float, false><<<B, bs, small_smem, st>>>(io, B, sc, guess, cs);
         }
     } else if (use_tc) {
         if (f64) {
-            CK(cudaFuncSetAttribute(solve_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-            solve_kernel<double, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota);
+            CK(cudaFuncSetAttribute(solve_kernel<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            solve_kernel<double, true, false><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota, cs);
         } else {
-            CK(cudaFuncSetAttribute(solve_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-            solve_kernel<float, true><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (float *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota);
+            CK(cudaFuncSetAttribute(solve_kernel<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            solve_kernel<float, true, false><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (float *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota, cs);
         }
+    } else if (obca) {
+        solve_kernel<double, false, true><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
+                                                             nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
     } else if (f64) {
-        solve_kernel<double, false><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
-                                                       nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota);
+        solve_kernel<double, false, false><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
+                                                              nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
     } else {
-        solve_kernel<float, false><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
-                                                      nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota);
+        solve_kernel<float, false, false><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
+                                                             nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
     }
     h->launches++;
     CK(cudaGetLastError());
-    return IGT_OK;
+    return end_call(h, st, f64 ? 2 : 1);
 }
 
+int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
+                  const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u_init, double *x,
+                  double *u, double *cost, double *viol, int *status, int *iters, void *stream)
+{
+    if (!h) return IGT_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return solve_dev_impl(h, B, x0, u_prev, curv, obs_xy, obs_psi, nn_ctx, u_init, x, u, cost, viol, status, iters, (cudaStream_t)stream);
+}
+
+// Host-pointer solve.  All inputs travel in ONE host-to-device copy and all outputs in ONE device-to-host copy on
+// the handle's own non-blocking stream: small batches (a closed-loop step solves B = 2) are packed into pinned
+// staging blocks first; large batches are copied array by array straight from the caller's (ideally pinned)
+// memory -- packing 100 MB on the host would cost more than the copies.
 int igt_solve_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
-                   const double *obs_xy, const double *nn_ctx, const double *u_init, double *x, double *u,
-                   double *cost, double *viol, int *status, int *iters)
+                   const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u_init, double *x,
+                   double *u, double *cost, double *viol, int *status, int *iters)
 {
     if (!h) return IGT_EINVAL;
     if (B < 0 || !x0 || !u_prev || !curv || !obs_xy || !x || !u || !cost || !viol || !status || !iters) {
         h->err = "igt_solve: null argument"; return IGT_EINVAL;
     }
     if (B == 0) return IGT_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (!h->hstream) CK(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    cudaStream_t st = h->hstream;
+    int rc = begin_call(h, st);
+    if (rc) return rc;
     const int N = h->prm.N;
     size_t nb = (size_t)B;
     size_t n_x0 = nb * 7, n_up = nb * 2, n_c = nb * 3, n_o = nb * (N + 1) * 2, n_ctx = nn_ctx ? nb * 4 : 0;
-    size_t n_ui = u_init ? nb * N * 2 : 0, n_x = nb * (N + 1) * 7, n_u = nb * N * 2;
-    size_t n_in = n_x0 + n_up + n_c + n_o + n_ctx + n_ui, n_out = n_x + n_u + 2 * nb;
-    size_t total = (n_in + n_out) * 8 + 2 * nb * 4;
-    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    size_t n_ui = u_init ? nb * N * 2 : 0, n_x = nb * (N + 1) * 7, n_u = nb * N * 2, n_op = obs_psi ? nb * (N + 1) : 0;
+    size_t n_in = n_x0 + n_up + n_c + n_o + n_ctx + n_ui + n_op, n_out = n_x + n_u + 2 * nb;
+    size_t in_bytes = n_in * 8, out_bytes = n_out * 8 + 2 * nb * 4, total = in_bytes + out_bytes;
+    rc = grow(h, &h->stage, &h->stage_bytes, total, st);
     if (rc) return rc;
     double *d = (double *)h->stage;
     double *dx0 = d, *dup = dx0 + n_x0, *dc = dup + n_up, *dob = dc + n_c, *dctx = dob + n_o, *dui = dctx + n_ctx;
-    double *dx = dui + n_ui, *du = dx + n_x, *dcost = du + n_u, *dviol = dcost + nb;
+    double *dop = dui + n_ui;
+    double *dx = dop + n_op, *du = dx + n_x, *dcost = du + n_u, *dviol = dcost + nb;
     int *dst = (int *)(dviol + nb), *dit = dst + nb;
-    cudaStream_t st = nullptr;
-    CK(cudaMemcpyAsync(dx0, x0, n_x0 * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dup, u_prev, n_up * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dc, curv, n_c * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dob, obs_xy, n_o * 8, cudaMemcpyHostToDevice, st));
-    if (nn_ctx) CK(cudaMemcpyAsync(dctx, nn_ctx, n_ctx * 8, cudaMemcpyHostToDevice, st));
-    if (u_init) CK(cudaMemcpyAsync(dui, u_init, n_ui * 8, cudaMemcpyHostToDevice, st));
-    rc = igt_solve_dev(h, B, dx0, dup, dc, dob, nn_ctx ? dctx : nullptr, u_init ? dui : nullptr, dx, du, dcost, dviol,
-                       dst, dit, st);
+    const bool packed = total <= (size_t)1 << 20;
+    if (packed) {
+        if (h->pin_bytes < total) {
+            if (h->pin) { CK(cudaStreamSynchronize(st)); CK(cudaFreeHost(h->pin)); h->pin = nullptr; h->pin_bytes = 0; }
+            CK(cudaHostAlloc(&h->pin, total, cudaHostAllocDefault));
+            h->pin_bytes = total;
+        }
+        double *p = (double *)h->pin;
+        memcpy(p, x0, n_x0 * 8); p += n_x0;
+        memcpy(p, u_prev, n_up * 8); p += n_up;
+        memcpy(p, curv, n_c * 8); p += n_c;
+        memcpy(p, obs_xy, n_o * 8); p += n_o;
+        if (nn_ctx) { memcpy(p, nn_ctx, n_ctx * 8); p += n_ctx; }
+        if (u_init) { memcpy(p, u_init, n_ui * 8); p += n_ui; }
+        if (obs_psi) { memcpy(p, obs_psi, n_op * 8); p += n_op; }
+        CK(cudaMemcpyAsync(dx0, h->pin, in_bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        CK(cudaMemcpyAsync(dx0, x0, n_x0 * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dup, u_prev, n_up * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dc, curv, n_c * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dob, obs_xy, n_o * 8, cudaMemcpyHostToDevice, st));
+        if (nn_ctx) CK(cudaMemcpyAsync(dctx, nn_ctx, n_ctx * 8, cudaMemcpyHostToDevice, st));
+        if (u_init) CK(cudaMemcpyAsync(dui, u_init, n_ui * 8, cudaMemcpyHostToDevice, st));
+        if (obs_psi) CK(cudaMemcpyAsync(dop, obs_psi, n_op * 8, cudaMemcpyHostToDevice, st));
+    }
+    rc = solve_dev_impl(h, B, dx0, dup, dc, dob, obs_psi ? dop : nullptr, nn_ctx ? dctx : nullptr, u_init ? dui : nullptr,
+                        dx, du, dcost, dviol, dst, dit, st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(x, dx, n_x * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(u, du, n_u * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(cost, dcost, nb * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(viol, dviol, nb * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(status, dst, nb * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(iters, dit, nb * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (packed) {
+        char *q = (char *)h->pin + in_bytes;
+        CK(cudaMemcpyAsync(q, dx, out_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(x, q, n_x * 8); q += n_x * 8;
+        memcpy(u, q, n_u * 8); q += n_u * 8;
+        memcpy(cost, q, nb * 8); q += nb * 8;
+        memcpy(viol, q, nb * 8); q += nb * 8;
+        memcpy(status, q, nb * 4); q += nb * 4;
+        memcpy(iters, q, nb * 4);
+    } else {
+        CK(cudaMemcpyAsync(x, dx, n_x * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(u, du, n_u * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cost, dcost, nb * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(viol, dviol, nb * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status, dst, nb * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(iters, dit, nb * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return IGT_OK;
 }
 
 int igt_eval_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
-                  const double *obs_xy, const double *nn_ctx, const double *u, double *cost, double *viol,
-                  double *z)
+                  const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u, double *cost,
+                  double *viol, double *z)
 {
     if (!h) return IGT_EINVAL;
     if (B < 0 || !x0 || !u_prev || !curv || !obs_xy || !u || !cost || !viol) { h->err = "igt_eval: null argument"; return IGT_EINVAL; }
     if (nn_ctx && !h->has_mlp) { h->err = "igt_eval: nn_ctx given but igt_set_mlp was never called"; return IGT_ENOMLP; }
     if (B == 0) return IGT_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int cs = 0;
+    { int rc0 = begin_call(h, nullptr); if (rc0) return rc0; }
     const int N = h->prm.N;
     size_t nb = (size_t)B;
     size_t n_x0 = nb * 7, n_up = nb * 2, n_c = nb * 3, n_o = nb * (N + 1) * 2, n_ctx = nn_ctx ? nb * 4 : 0;
-    size_t n_u = nb * N * 2, n_z = nb * (N + 1) * 7;
-    size_t total = (n_x0 + n_up + n_c + n_o + n_ctx + n_u + n_z + 2 * nb) * 8;
-    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    size_t n_u = nb * N * 2, n_z = nb * (N + 1) * 7, n_op = obs_psi ? nb * (N + 1) : 0;
+    size_t total = (n_x0 + n_up + n_c + n_o + n_ctx + n_u + n_z + 2 * nb + n_op) * 8;
+    int rc = grow(h, &h->stage, &h->stage_bytes, total, nullptr);
     if (rc) return rc;
-    if (nn_ctx) { rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * B * 8); if (rc) return rc; }
+    if (nn_ctx) { rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * B * 8, nullptr); if (rc) return rc; }
     double *d = (double *)h->stage;
     double *dx0 = d, *dup = dx0 + n_x0, *dc = dup + n_up, *dob = dc + n_c, *dctx = dob + n_o, *du = dctx + n_ctx;
-    double *dz = du + n_u, *dcost = dz + n_z, *dviol = dcost + nb;
+    double *dz = du + n_u, *dcost = dz + n_z, *dviol = dcost + nb, *dop = dviol + nb;
+    if (obs_psi) CK(cudaMemcpy(dop, obs_psi, n_op * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dx0, x0, n_x0 * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dup, u_prev, n_up * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dc, curv, n_c * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dob, obs_xy, n_o * 8, cudaMemcpyHostToDevice));
     if (nn_ctx) CK(cudaMemcpy(dctx, nn_ctx, n_ctx * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(du, u, n_u * 8, cudaMemcpyHostToDevice));
-    rc = upload_params(h, nullptr, false, true);
+    rc = acquire_cslot(h, 1, nullptr, &cs);
     if (rc) return rc;
     int bs = 128, gs = (B + bs - 1) / bs;
     eval_kernel<<<gs, bs>>>(B, dx0, dup, dc, dob, nn_ctx ? dctx : nullptr, du, dcost, dviol, dz,
-                            nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width);
+                            nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, cs, obs_psi ? dop : nullptr);
     h->launches++;
     CK(cudaGetLastError());
+    rc = end_call(h, nullptr, 2);
+    if (rc) return rc;
     CK(cudaMemcpy(cost, dcost, nb * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(viol, dviol, nb * 8, cudaMemcpyDeviceToHost));
     if (z) CK(cudaMemcpy(z, dz, n_z * 8, cudaMemcpyDeviceToHost));
@@ -636,7 +802,10 @@ int igt_measure_fma_peak(igt_handle *h, int precision, double *tflops)
 {
     if (!h || !tflops) return IGT_EINVAL;
     const int blocks = h->n_sm * 8, threads = 256, iters = 1 << 16;
-    int rc = grow(h, &h->stage, &h->stage_bytes, (size_t)blocks * threads * 8);
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = begin_call(h, nullptr);
+    if (rc) return rc;
+    rc = grow(h, &h->stage, &h->stage_bytes, (size_t)blocks * threads * 8, nullptr);
     if (rc) return rc;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -653,6 +822,8 @@ int igt_measure_fma_peak(igt_handle *h, int precision, double *tflops)
         h->launches++;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    rc = end_call(h, nullptr, 0);
+    if (rc) return rc;
     *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
     return IGT_OK;
 }
@@ -665,8 +836,12 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
     if (!h->has_mlp) { h->err = "igt_mlp_value: igt_set_mlp was never called"; return IGT_ENOMLP; }
     if (use_tensor_cores && !h->tc.enabled) { h->err = "igt_mlp_value: tensor-core path needs a 6-128-128-1 network"; return IGT_EINVAL; }
     if (B == 0) return IGT_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int cs = 0;
+    int rc = begin_call(h, nullptr);
+    if (rc) return rc;
     size_t nb = (size_t)B, total = (nb * 2 + nb * 4 + nb * 6) * 8;
-    int rc = grow(h, &h->stage, &h->stage_bytes, total);
+    rc = grow(h, &h->stage, &h->stage_bytes, total, nullptr);
     if (rc) return rc;
     double *ds = (double *)h->stage, *dv = ds + nb, *dc = dv + nb, *dout = dc + nb * 4;
     CK(cudaMemcpy(ds, sN, nb * 8, cudaMemcpyHostToDevice));
@@ -677,14 +852,16 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
         if (grid > h->n_sm) grid = h->n_sm;
         mlp_tc_kernel<<<grid, 256, TC_SMEM_BYTES>>>(h->tc, B, ds, dv, dc, dout);
     } else {
-        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * nb * 8);
+        rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * nb * 8, nullptr);
         if (rc) return rc;
-        rc = upload_params(h, nullptr, false, true);
+        rc = acquire_cslot(h, 1, nullptr, &cs);
         if (rc) return rc;
-        mlp_ref_kernel<<<(int)((nb + 127) / 128), 128>>>(B, ds, dv, dc, dout, (double *)h->mlp_scratch, h->mlp_width);
+        mlp_ref_kernel<<<(int)((nb + 127) / 128), 128>>>(B, ds, dv, dc, dout, (double *)h->mlp_scratch, h->mlp_width, cs);
     }
     h->launches++;
     CK(cudaGetLastError());
+    rc = end_call(h, nullptr, use_tensor_cores ? 0 : 2);
+    if (rc) return rc;
     CK(cudaMemcpy(out, dout, nb * 48, cudaMemcpyDeviceToHost));
     return IGT_OK;
 }

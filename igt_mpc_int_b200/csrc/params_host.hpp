@@ -26,6 +26,7 @@ inline void fill_dev_params(const igt_params &p, DevParams<T> &d)
     d.reg_min = T(p.reg_min); d.reg_up = T(p.reg_up); d.reg_down = T(p.reg_down); d.reg_max = T(p.reg_max);
     d.reg_jump = T(p.reg_jump);
     d.eps_phi = T(p.eps_phi); d.gamma_theta = T(p.gamma_theta); d.theta_small = T(p.theta_small);
+    d.acc_tol = T(p.acc_tol); d.acc_rp = T(p.acc_rp); d.acc_comp = T(p.acc_comp); d.x0_tol = T(p.x0_tol);
     for (int m = 0; m < p.n_cinf; m++) {
         d.cinf_A[m][0] = T(p.cinf_A[m][0]); d.cinf_A[m][1] = T(p.cinf_A[m][1]); d.cinf_b[m] = T(p.cinf_b[m]);
     }
@@ -46,6 +47,7 @@ inline int default_params(igt_params *p, int precision)
     p->mu0_warm = 1e-4; p->y_init_min_warm = 1e-3;
     p->stall_iter = 16; p->stall_rp = 1e-2; p->max_trials = 0;
     p->precision = precision;
+    p->acc_tol = 1e-3; p->acc_rp = 1e-6; p->acc_comp = 1e-4; p->x0_tol = 1e-6;
     if (precision == IGT_PREC_F64) {
         p->tol = 1e-6; p->tol_rp = 1e-8; p->tol_comp = 1e-7; p->mu_floor = 1e-8;
         p->eps_phi = 1e-12; p->theta_small = 1e-10;

@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdint>
 #include "mlp_tc.cuh"
+#include "obca.cuh"
 
 #ifdef __CUDACC__
 #define IGT_HD __host__ __device__ __forceinline__
@@ -48,6 +49,9 @@ constexpr int MAX_CINF = 128;
 // w = (zeta, u) and, together with the dynamics second-order term, 22 entries of the symmetric
 // w-space Hessian; these are what the sequential sweeps need from a node.
 constexpr int NGE = 8, NHE = 22;
+// OBCA collision mode (obca.cuh): the row's gradient has a heading entry as well -> one more gradient entry (psi) and
+// two more Hessian entries ((x, psi), (y, psi)); they are appended, so the circle mode's tables are a prefix.
+constexpr int NGE_OBCA = 9, NHE_OBCA = 24;
 // Iterate buffers per workspace slot: the current iterate plus one buffer per step halving of a line
 // search, so that all candidates alpha, alpha/2, ... of an iteration can be rolled out at once when
 // lanes are idle (speculative line search, see trial_phase_cta).  Candidate j of an iterate living in
@@ -67,6 +71,7 @@ struct DevParams {
     T v_min, v_max, a_min, a_max, df_max, ey_lim, da_max, ddf_max, d_min, w_u;
     T tol, tol_rp, tol_comp, mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min, mu0_warm, y_init_min_warm, alpha_safety, stall_rp;
     T reg_min, reg_up, reg_down, reg_max, reg_jump, eps_phi, gamma_theta, theta_small;
+    T acc_tol, acc_rp, acc_comp, x0_tol;
     T cinf_A[MAX_CINF][2], cinf_b[MAX_CINF];
     T Wn[36], mu_f[6], sigma_t, mu_t;
     const T *W[MAX_MLP_LAYERS], *b[MAX_MLP_LAYERS];   // device pointers, row-major [out][in]
@@ -88,7 +93,7 @@ IGT_HD int row_total(int N, int n_cinf) { return row_off(N, n_cinf, N) + 3; }
 struct WsLayout {
     int N, M;
     int oZ[NBUF], oU[NBUF], oY[NBUF], oS[NBUF], oTc, oSens, oLam, oKu, oKK, oGw, oRed, oGl, oHl, oTr, oDu, total;
-    IGT_HD void init(int N_, int n_cinf)
+    IGT_HD void init(int N_, int n_cinf, int nge = NGE, int nhe = NHE)
     {
         N = N_;
         M = row_total(N, n_cinf);
@@ -101,10 +106,10 @@ struct WsLayout {
         oLam = o;  o += NZ * (N + 1);
         oKu = o;   o += 2 * N;
         oKK = o;   o += 2 * NA * N;
-        oGw = o;   o += NGE * (N + 1);     // node-local row summaries, see node_phase1 / node_phase2
+        oGw = o;   o += nge * (N + 1);     // node-local row summaries, see node_phase1 / node_phase2
         oRed = o;  o += 4 * (N + 1);
-        oGl = o;   o += NGE * (N + 1);
-        oHl = o;   o += NHE * (N + 1);
+        oGl = o;   o += nge * (N + 1);
+        oHl = o;   o += nhe * (N + 1);
         oTr = o;   o += NBUF * 3 * (N + 1);  // per-node results of a trial step, see node_phase3
         oDu = o;   o += NBUF * 2 * N;        // control change of a trial step (exact, not new - old)
         oTc = o;   o += NBUF * NTC;          // per-candidate rollout results: finite flag, cost, value term (6)
@@ -118,10 +123,13 @@ struct WsLayout {
 // offset that is a compile-time constant folds into the load/store immediate.
 // STRIDE 1 is the latency path for batches of at most one problem per SM: the workspace of the CTA's one
 // problem lives in shared memory, contiguously (bind ignores the slot, nothing is prefetched).
-template <typename T, int STRIDE = 32>
+template <typename T, int STRIDE = 32, bool OBCA = false>
 struct Ws {
+    static constexpr bool obca = OBCA;
+    static constexpr int nge = OBCA ? NGE_OBCA : NGE, nhe = OBCA ? NHE_OBCA : NHE;
     T *wb;          // base + (slot / 32) * total * 32 + slot % 32
     WsLayout L;
+    IGT_HD void init_layout(int N, int n_cinf) { L.init(N, n_cinf, nge, nhe); }
     IGT_HD void bind(T *base, long slot) { wb = STRIDE == 32 ? base + (slot / 32) * (long)L.total * 32 + (slot % 32) : base; }
     IGT_HD T &at(int e) const { return wb[e * STRIDE]; }
     IGT_HD void pf(int e) const
@@ -138,10 +146,10 @@ struct Ws {
     IGT_HD T &Lam(int k, int i) const { return at(L.oLam + k * NZ + i); }
     IGT_HD T &ku(int k, int i) const { return at(L.oKu + k * 2 + i); }
     IGT_HD T &KK(int k, int i, int j) const { return at(L.oKK + (k * 2 + i) * NA + j); }
-    IGT_HD T &Gw(int k, int e) const { return at(L.oGw + k * NGE + e); }
+    IGT_HD T &Gw(int k, int e) const { return at(L.oGw + k * nge + e); }
     IGT_HD T &Red(int k, int e) const { return at(L.oRed + k * 4 + e); }
-    IGT_HD T &Gl(int k, int e) const { return at(L.oGl + k * NGE + e); }
-    IGT_HD T &Hl(int k, int e) const { return at(L.oHl + k * NHE + e); }
+    IGT_HD T &Gl(int k, int e) const { return at(L.oGl + k * nge + e); }
+    IGT_HD T &Hl(int k, int e) const { return at(L.oHl + k * nhe + e); }
     IGT_HD T &Tr(int b, int k, int e) const { return at(L.oTr + (b * (L.N + 1) + k) * 3 + e); }
     IGT_HD T &Du(int b, int k, int i) const { return at(L.oDu + (b * L.N + k) * 2 + i); }
     IGT_HD T &Tc(int b, int e) const { return at(L.oTc + b * NTC + e); }
@@ -152,6 +160,7 @@ struct ProbIO {
     const double *x0, *u_prev, *curv, *obs, *ctx, *u_init;   // [B,7] [B,2] [B,3] [B,N+1,2] [B,4] [B,N,2]
     double *x, *u, *cost, *viol;
     int *status, *iters;
+    const double *obs_psi = nullptr;                         // [B,N+1] obstacle heading forecast: OBCA collision rows
 };
 
 // ------------------------------------------------------------------ dynamics -----------
@@ -522,8 +531,9 @@ struct LogSum {
 
 // ------------------------------------------------------------------ rows ---------------
 // visit every inequality row of stage k (k == N: terminal node) in workspace order.
-// f(IC<slot>, r, c, IC<i0>, g0, IC<i1>, g1, hxx, hxy, hyy): value, up to two gradient entries in
-// w = (zeta, u) (i1 < 0: single entry), 2x2 Hessian block on (x, y) (collision row only).
+// f(IC<slot>, r, c, IC<i0>, g0, IC<i1>, g1, IC<i2>, g2, hxx, hxy, hyy): value, up to three gradient entries in
+// w = (zeta, u) (i1 / i2 < 0: unused; the third is the heading entry of the OBCA row), 2x2 Hessian block on (x, y)
+// (circle collision row only).
 // The indices travel as types so that every use indexes registers statically.  `slot` is the row's
 // fixed register slot (0,1 speed; 2,3 ey; 4 collision; 5..12 input and rate rows), the same for every
 // stage.  The terminal-set rows of stage N-1 (slot -1) are visited only if CINF; the node phases run
@@ -533,41 +543,46 @@ constexpr int NSLOT = 13;
 IGT_HD int slot_base(int N, int k) { return k == 0 ? 5 : (k == N ? 2 : 0); }      // workspace row = slot - base
 IGT_HD bool slot_used(int N, int k, int slot) { return k == 0 ? slot >= 5 : (k == N ? (slot >= 2 && slot <= 4) : true); }
 
-template <bool CINF = true, typename T, typename F>
-IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, const T *u, T ox, T oy, F &&f)
+template <bool CINF = true, bool OBCA = false, typename T, typename F>
+IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, const T *u, T ox, T oy, T opsi, F &&f)
 {
     const T Z0 = T(0);
+    using NO = IC<-1>;
     int r = 0;
     if (k >= 1) {
         if (k < P.N) {
-            f(IC<0>{}, r++, z[IV] - P.v_max, IC<IV>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:317
-            f(IC<1>{}, r++, P.v_min - z[IV], IC<IV>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);     // mpc.py:316
+            f(IC<0>{}, r++, z[IV] - P.v_max, IC<IV>{}, T(1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);      // mpc.py:317
+            f(IC<1>{}, r++, P.v_min - z[IV], IC<IV>{}, T(-1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);     // mpc.py:316
         }
-        f(IC<2>{}, r++, z[IEY] - P.ey_lim, IC<IEY>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);      // mpc.py:298
-        f(IC<3>{}, r++, -P.ey_lim - z[IEY], IC<IEY>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);    // mpc.py:299
-        {   // mpc.py:226 in the equivalent distance form d_min - |p - o| <= 0
+        f(IC<2>{}, r++, z[IEY] - P.ey_lim, IC<IEY>{}, T(1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);      // mpc.py:298
+        f(IC<3>{}, r++, -P.ey_lim - z[IEY], IC<IEY>{}, T(-1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);    // mpc.py:299
+        if constexpr (!OBCA) {   // mpc.py:226 in the equivalent distance form d_min - |p - o| <= 0
             T dx = z[IX] - ox, dy = z[IY] - oy;
             T dist = sqrt(dx * dx + dy * dy);
             dist = dist < T(1e-9) ? T(1e-9) : dist;
             T id = T(1) / dist, nx = dx * id, ny = dy * id;
-            f(IC<4>{}, r++, P.d_min - dist, IC<IX>{}, -nx, IC<IY>{}, -ny, -(T(1) - nx * nx) * id, nx * ny * id, -(T(1) - ny * ny) * id);
+            f(IC<4>{}, r++, P.d_min - dist, IC<IX>{}, -nx, IC<IY>{}, -ny, NO{}, Z0, -(T(1) - nx * nx) * id, nx * ny * id, -(T(1) - ny * ny) * id);
+        } else {                 // mpc.py:211-221 with the duals maximised out (obca.cuh): margin - signed rectangle distance
+            T gd[3];
+            const T sd = obca_rect_sdist(z[IX], z[IY], z[IPSI], ox, oy, opsi, gd);
+            f(IC<4>{}, r++, P.d_min + T(OBCA_MARGIN) - sd, IC<IX>{}, -gd[0], IC<IY>{}, -gd[1], IC<IPSI>{}, -gd[2], Z0, Z0, Z0);
         }
     }
     if (k == P.N) return;
-    f(IC<5>{}, r++, u[0] - P.a_max, IC<IUA>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);             // mpc.py:319
-    f(IC<6>{}, r++, P.a_min - u[0], IC<IUA>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:318
-    f(IC<7>{}, r++, u[1] - P.df_max, IC<IUD>{}, T(1), IC<-1>{}, Z0, Z0, Z0, Z0);            // mpc.py:321
-    f(IC<8>{}, r++, -P.df_max - u[1], IC<IUD>{}, T(-1), IC<-1>{}, Z0, Z0, Z0, Z0);          // mpc.py:320
+    f(IC<5>{}, r++, u[0] - P.a_max, IC<IUA>{}, T(1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);             // mpc.py:319
+    f(IC<6>{}, r++, P.a_min - u[0], IC<IUA>{}, T(-1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);            // mpc.py:318
+    f(IC<7>{}, r++, u[1] - P.df_max, IC<IUD>{}, T(1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);            // mpc.py:321
+    f(IC<8>{}, r++, -P.df_max - u[1], IC<IUD>{}, T(-1), NO{}, Z0, NO{}, Z0, Z0, Z0, Z0);          // mpc.py:320
     T da = u[0] - up[0], dd = u[1] - up[1];
-    f(IC<9>{}, r++, da - P.da_max, IC<IPA>{}, T(-1), IC<IUA>{}, T(1), Z0, Z0, Z0);          // mpc.py:303-311
-    f(IC<10>{}, r++, -da - P.da_max, IC<IPA>{}, T(1), IC<IUA>{}, T(-1), Z0, Z0, Z0);
-    f(IC<11>{}, r++, dd - P.ddf_max, IC<IPD>{}, T(-1), IC<IUD>{}, T(1), Z0, Z0, Z0);
-    f(IC<12>{}, r++, -dd - P.ddf_max, IC<IPD>{}, T(1), IC<IUD>{}, T(-1), Z0, Z0, Z0);
+    f(IC<9>{}, r++, da - P.da_max, IC<IPA>{}, T(-1), IC<IUA>{}, T(1), NO{}, Z0, Z0, Z0, Z0);          // mpc.py:303-311
+    f(IC<10>{}, r++, -da - P.da_max, IC<IPA>{}, T(1), IC<IUA>{}, T(-1), NO{}, Z0, Z0, Z0, Z0);
+    f(IC<11>{}, r++, dd - P.ddf_max, IC<IPD>{}, T(-1), IC<IUD>{}, T(1), NO{}, Z0, Z0, Z0, Z0);
+    f(IC<12>{}, r++, -dd - P.ddf_max, IC<IPD>{}, T(1), IC<IUD>{}, T(-1), NO{}, Z0, Z0, Z0, Z0);
     if (CINF && k == P.N - 1)
 #pragma unroll 1
         for (int m = 0; m < P.n_cinf; m++)                                          // mpc.py:177-180
             f(IC<-1>{}, r++, P.cinf_A[m][0] * z[IV] + P.cinf_A[m][1] * u[0] - P.cinf_b[m], IC<IV>{}, P.cinf_A[m][0], IC<IUA>{},
-              P.cinf_A[m][1], Z0, Z0, Z0);
+              P.cinf_A[m][1], NO{}, Z0, Z0, Z0, Z0);
 }
 
 // prefetch the slacks (and multipliers) of all rows of node k of iterate buffer b into L1, issued before
@@ -582,12 +597,32 @@ IGT_HD void prefetch_rows(const DevParams<T> &P, const W &w, int k, int b, int o
     }
 }
 
-// the terminal-set rows of stage N-1 (mpc.py:177-180; workspace rows o + 13 ...): f(r, A0, A1, b) per row
-template <typename T, typename F>
-IGT_HD void cinf_rows(const DevParams<T> &P, int o, F &&f)
+// the terminal-set rows of stage N-1 (mpc.py:177-180; workspace rows o + 13 ...) of iterate buffer b:
+// f(r, A0, A1, b, s, y) per row.  IGT_CINF_BATCH: multipliers and slacks are loaded eight rows at a time before
+// the rows' arithmetic (one exposed memory latency per group instead of one per row).
+#ifndef IGT_CINF_BATCH
+#define IGT_CINF_BATCH 0
+#endif
+template <typename T, typename W, typename F>
+IGT_HD void cinf_rows(const DevParams<T> &P, const W &w, int b, int o, F &&f)
 {
+#if !IGT_CINF_BATCH
 #pragma unroll 1
-    for (int m = 0; m < P.n_cinf; m++) f(o + NSLOT + m, P.cinf_A[m][0], P.cinf_A[m][1], P.cinf_b[m]);
+    for (int m = 0; m < P.n_cinf; m++)
+        f(o + NSLOT + m, P.cinf_A[m][0], P.cinf_A[m][1], P.cinf_b[m], w.S(b, o + NSLOT + m), w.Y(b, o + NSLOT + m));
+#else
+#pragma unroll 1
+    for (int m0 = 0; m0 < P.n_cinf; m0 += 8) {
+        T s8[8], y8[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (m0 + j < P.n_cinf) { s8[j] = w.S(b, o + NSLOT + m0 + j); y8[j] = w.Y(b, o + NSLOT + m0 + j); }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (m0 + j < P.n_cinf)
+                f(o + NSLOT + m0 + j, P.cinf_A[m0 + j][0], P.cinf_A[m0 + j][1], P.cinf_b[m0 + j], s8[j], y8[j]);
+    }
+#endif
 }
 
 // symmetric 11x11 / 9x9 storage (upper triangle, row-major)
@@ -672,28 +707,28 @@ IGT_HD void add_dyn_hessian(const DevParams<T> &P, const T *z, const T *u, const
 // use indexes registers statically after unrolling)
 IGT_HD constexpr int ge_idx(int e)
 {
-    return e == 0 ? IV : e == 1 ? IEY : e == 2 ? IX : e == 3 ? IY : e == 4 ? IUA : e == 5 ? IUD : e == 6 ? IPA : IPD;
+    return e == 0 ? IV : e == 1 ? IEY : e == 2 ? IX : e == 3 ? IY : e == 4 ? IUA : e == 5 ? IUD : e == 6 ? IPA : e == 7 ? IPD : IPSI;
 }
 IGT_HD constexpr int he_i(int e)
 {
     return e == 0 ? IV : e == 1 ? IEY : e == 2 ? IX : e == 3 ? IX : e == 4 ? IY : e == 5 ? IUA : e == 6 ? IUD
          : e == 7 ? IPA : e == 8 ? IPA : e == 9 ? IPD : e == 10 ? IPD : e == 11 ? IV
          : e == 12 ? IEY : e == 13 ? IEPSI : e == 14 ? IPSI : e == 15 ? IEY : e == 16 ? IEPSI : e == 17 ? IV
-         : e == 18 ? IEY : e == 19 ? IEPSI : e == 20 ? IPSI : IV;
+         : e == 18 ? IEY : e == 19 ? IEPSI : e == 20 ? IPSI : e == 21 ? IV : e == 22 ? IX : IY;
 }
 IGT_HD constexpr int he_j(int e)
 {
     return e == 0 ? IV : e == 1 ? IEY : e == 2 ? IX : e == 3 ? IY : e == 4 ? IY : e == 5 ? IUA : e == 6 ? IUD
          : e == 7 ? IPA : e == 8 ? IUA : e == 9 ? IPD : e == 10 ? IUD : e == 11 ? IUA
          : e == 12 ? IEPSI : e == 13 ? IEPSI : e == 14 ? IPSI : e == 15 ? IV : e == 16 ? IV : e == 17 ? IPSI
-         : e == 18 ? IUD : e == 19 ? IUD : e == 20 ? IUD : IUD;
+         : e == 18 ? IUD : e == 19 ? IUD : e == 20 ? IUD : e == 21 ? IUD : IPSI;
 }
 
 // what a node phase needs to know about the problem it works for
 template <typename T>
 struct NodeCtx {
     T curv[3], uprev[2], mu, alpha;
-    const double *obs, *x0p;
+    const double *obs, *x0p, *obs_psi;    // obs_psi: this problem's [N+1] obstacle headings (OBCA mode) or null
     int cur, second_order, ls;
 };
 
@@ -729,19 +764,20 @@ IGT_HD void node_phase1(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
 #pragma unroll
     for (int i = 0; i < NW; i++) gw[i] = T(0);
     T rp = T(0), s_max = T(0), sy_min = T(1e30), sy_max = T(0);
-    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
-        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+    visit_rows<false, W::obca>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), W::obca ? T(c.obs_psi[k]) : T(0),
+                               [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, auto I2, T g2, T, T, T) {
+        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
         const T s = w.S(b, o + r), y = w.Y(b, o + r);
         gw[i0] += g0 * s;
         if constexpr (i1 >= 0) gw[i1] += g1 * s;
+        if constexpr (i2 >= 0) gw[i2] += g2 * s;
         rp = fmax(rp, fabs(cv + y));
         s_max = fmax(s_max, s);
         T sy = s * y;
         sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
     });
     if (k == N - 1)
-        cinf_rows(P, o, [&](int r, T A0, T A1, T bb) {
-            const T s = w.S(b, r), y = w.Y(b, r);
+        cinf_rows(P, w, b, o, [&](int, T A0, T A1, T bb, T s, T y) {
             const T cv = A0 * z[IV] + A1 * u[0] - bb;
             gw[IV] += A0 * s; gw[IUA] += A1 * s;
             rp = fmax(rp, fabs(cv + y));
@@ -750,7 +786,7 @@ IGT_HD void node_phase1(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
             sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
         });
 #pragma unroll
-    for (int e = 0; e < NGE; e++) w.Gw(k, e) = gw[ge_idx(e)];
+    for (int e = 0; e < W::nge; e++) w.Gw(k, e) = gw[ge_idx(e)];
     w.Red(k, 0) = rp; w.Red(k, 1) = s_max; w.Red(k, 2) = sy_min; w.Red(k, 3) = sy_max;
 }
 
@@ -777,8 +813,9 @@ IGT_HD void node_phase2(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
         for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
         add_dyn_hessian(P, z, u, c.curv, ln, H);
     }
-    visit_rows<false>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, T hxx, T hxy, T hyy) {
-        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+    visit_rows<false, W::obca>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), W::obca ? T(c.obs_psi[k]) : T(0),
+                               [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, auto I2, T g2, T hxx, T hxy, T hyy) {
+        constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
         const T s = w.S(b, o + r), y = w.Y(b, o + r);
         T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
         g[i0] += g0 * gr;
@@ -788,13 +825,18 @@ IGT_HD void node_phase2(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
             H[sym11(i1, i1)] += sig * g1 * g1;
             H[sym11(i0, i1)] += sig * g0 * g1;
         }
-        if constexpr (i0 == IX) {
+        if constexpr (i2 >= 0) {                                  // OBCA row: heading entry, Gauss-Newton (no row Hessian)
+            g[i2] += g2 * gr;
+            H[sym11(i2, i2)] += sig * g2 * g2;
+            H[sym11(i0, i2)] += sig * g0 * g2;
+            H[sym11(i1, i2)] += sig * g1 * g2;
+        }
+        if constexpr (i0 == IX && i2 < 0) {
             H[sym11(IX, IX)] += s * hxx; H[sym11(IX, IY)] += s * hxy; H[sym11(IY, IY)] += s * hyy;
         }
     });
     if (k == N - 1)
-        cinf_rows(P, o, [&](int r, T A0, T A1, T bb) {
-            const T s = w.S(b, r), y = w.Y(b, r);
+        cinf_rows(P, w, b, o, [&](int, T A0, T A1, T bb, T s, T y) {
             const T cv = A0 * z[IV] + A1 * u[0] - bb;
             T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
             g[IV] += A0 * gr;
@@ -804,9 +846,9 @@ IGT_HD void node_phase2(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
             H[sym11(IV, IUA)] += sig * A0 * A1;
         });
 #pragma unroll
-    for (int e = 0; e < NGE; e++) w.Gl(k, e) = g[ge_idx(e)];
+    for (int e = 0; e < W::nge; e++) w.Gl(k, e) = g[ge_idx(e)];
 #pragma unroll
-    for (int e = 0; e < NHE; e++) w.Hl(k, e) = H[sym11(he_i(e), he_j(e))];
+    for (int e = 0; e < W::nhe; e++) w.Hl(k, e) = H[sym11(he_i(e), he_j(e))];
 }
 
 // Closed-loop nonlinear rollout of candidate j of the line search (step alpha / 2^j) from the
@@ -881,14 +923,15 @@ IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
     if (k < N) { un[0] = w.U(nb, k, 0); un[1] = w.U(nb, k, 1); } else { un[0] = un[1] = T(0); }
     dw[IPA] = upn[0] - up[0]; dw[IPD] = upn[1] - up[1];
     if (k < N) { dw[IUA] = w.Du(nb, k, 0); dw[IUD] = w.Du(nb, k, 1); } else { dw[IUA] = dw[IUD] = T(0); }
-    const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]);
+    const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]), opsi = W::obca ? T(c.obs_psi[k]) : T(0);
     bool fail = false;
     T ynv[NSLOT];
-    visit_rows<false>(P, k, z, up, u, ox, oy, [&](auto SL, int r, T cv, auto I0, T g0, auto I1, T g1, T, T, T) {
-        constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+    visit_rows<false, W::obca>(P, k, z, up, u, ox, oy, opsi, [&](auto SL, int r, T cv, auto I0, T g0, auto I1, T g1, auto I2, T g2, T, T, T) {
+        constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
         const T s = w.S(b, o + r), y = w.Y(b, o + r);
         T dc = g0 * dw[i0];
         if constexpr (i1 >= 0) dc += g1 * dw[i1];
+        if constexpr (i2 >= 0) dc += g2 * dw[i2];
         T yn = y - alpha * (cv + y) - dc;
         T sn = s + (alpha * (s * cv + mu) + s * dc) / y;
         if (yn < (T(1) - tau) * y) fail = true;                 // fraction to the boundary
@@ -901,14 +944,13 @@ IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
     T th = T(0);
     LogSum<T> lg;
     if (!fail)
-        visit_rows<false>(P, k, zn, upn, un, ox, oy, [&](auto SL, int, T cv, auto, T, auto, T, T, T, T) {
+        visit_rows<false, W::obca>(P, k, zn, upn, un, ox, oy, opsi, [&](auto SL, int, T cv, auto, T, auto, T, auto, T, T, T, T) {
             constexpr int sl = decltype(SL)::value;
             th += fabs(cv + ynv[sl]);
             lg.add(ynv[sl]);
         });
     if (k == N - 1)
-        cinf_rows(P, o, [&](int r, T A0, T A1, T bb) {
-            const T s = w.S(b, r), y = w.Y(b, r);
+        cinf_rows(P, w, b, o, [&](int r, T A0, T A1, T bb, T s, T y) {
             const T cv = A0 * z[IV] + A1 * u[0] - bb;
             T dc = A0 * dw[IV];
             dc += A1 * dw[IUA];
@@ -925,10 +967,12 @@ IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
 // ------------------------------------------------------------------ the solver ---------
 template <typename T, typename W = Ws<T>>
 struct Solver {
+    static constexpr bool obca = W::obca;
     const DevParams<T> &P;
     W w;
     T x0[NZ], uprev[2], curv[3], ctx[4];
     const double *obs;        // this problem's [N+1][2] forecast (AoS, read-only)
+    const double *obs_psi = nullptr;   // this problem's [N+1] obstacle headings (OBCA mode)
     const double *x0p;        // this problem's x0[7] in the caller's array
     bool gt;                  // gt_mpc terminal cost
     T *mlp_scratch;           // [2][6][width] when gt (per-thread slab), else null
@@ -949,6 +993,15 @@ struct Solver {
 
     IGT_HD T ox(int k) const { return T(obs[2 * k]); }
     IGT_HD T oy(int k) const { return T(obs[2 * k + 1]); }
+    IGT_HD T opsi(int k) const { return W::obca ? T(obs_psi[k]) : T(0); }
+    // value of the collision row of node k at (x, y, psi) in the units the reference writes it in:
+    // circle mpc.py:226 d_min^2 - |p - o|^2; OBCA mpc.py:216 d_min + 1e-6 - (dual value = rectangle distance)
+    IGT_HD T collision_row_ref(int k, T x, T y, T psi) const
+    {
+        if (W::obca) { T gd[3]; return P.d_min + T(OBCA_MARGIN) - obca_rect_sdist(x, y, psi, ox(k), oy(k), opsi(k), gd); }
+        const T dx = x - ox(k), dy = y - oy(k);
+        return P.d_min * P.d_min - dx * dx - dy * dy;
+    }
 
     // terminal value -(cost contribution): 'mpc' V = s_N - s_0 ; 'gt_mpc' V = MLP
     IGT_HD void terminal_value(T sN, T vN, TermVal<T> &t, bool want_deriv)
@@ -1014,12 +1067,12 @@ struct Solver {
         w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1);
         if (riccati) {
 #pragma unroll
-            for (int e = 0; e < NGE; e++) w.pf(w.L.oGl + k * NGE + e);
+            for (int e = 0; e < W::nge; e++) w.pf(w.L.oGl + k * W::nge + e);
 #pragma unroll
-            for (int e = 0; e < NHE; e++) w.pf(w.L.oHl + k * NHE + e);
+            for (int e = 0; e < W::nhe; e++) w.pf(w.L.oHl + k * W::nhe + e);
         } else {
 #pragma unroll
-            for (int e = 0; e < NGE; e++) w.pf(w.L.oGw + k * NGE + e);
+            for (int e = 0; e < W::nge; e++) w.pf(w.L.oGw + k * W::nge + e);
 #pragma unroll
             for (int e = 0; e < 4; e++) w.pf(w.L.oRed + k * 4 + e);
         }
@@ -1070,8 +1123,8 @@ struct Solver {
             J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
             if (k + 1 < N) viol += fmax(T(0), z[IV] - P.v_max) + fmax(T(0), P.v_min - z[IV]);
             viol += fmax(T(0), fabs(z[IEY]) - P.ey_lim);
-            T dx = z[IX] - ox(k + 1), dy = z[IY] - oy(k + 1);
-            viol += fmax(T(0), P.d_min - sqrt(dx * dx + dy * dy));
+            if (W::obca) viol += fmax(T(0), collision_row_ref(k + 1, z[IX], z[IY], z[IPSI]));
+            else { T dx = z[IX] - ox(k + 1), dy = z[IY] - oy(k + 1); viol += fmax(T(0), P.d_min - sqrt(dx * dx + dy * dy)); }
         }
         J += P.w_u * su - (z[IS] - x0[IS]);
         return J + T(100) * viol;
@@ -1084,6 +1137,7 @@ struct Solver {
         uprev[0] = T(io.u_prev[p * 2]); uprev[1] = T(io.u_prev[p * 2 + 1]);
         for (int i = 0; i < 3; i++) curv[i] = T(io.curv[p * 3 + i]);
         obs = io.obs + p * (P.N + 1) * 2;
+        if (W::obca) obs_psi = io.obs_psi + p * (P.N + 1);
         gt = has_ctx;
         if (gt) for (int i = 0; i < 4; i++) ctx[i] = T(io.ctx[p * 4 + i]);
     }
@@ -1112,7 +1166,7 @@ struct Solver {
         mu = warm ? P.mu0_warm : P.mu0; reg = T(0); alpha = T(1); reg_hint = T(0);
         const T y_min = warm ? P.y_init_min_warm : P.y_init_min;
         {   // rows on x0 alone: mpc.py:316-317 and :298-299 at k = 0
-            T tol = T(1e-9);
+            const T tol = P.x0_tol;
             if (!(x0[IV] >= P.v_min - tol && x0[IV] <= P.v_max + tol && fabs(x0[IEY]) <= P.ey_lim + tol)) {
                 status = 2; done = true;
                 return false;
@@ -1137,7 +1191,7 @@ struct Solver {
             if (k < N) { u[0] = w.U(0, k, 0); u[1] = w.U(0, k, 1); su += u[0] * u[0] + u[1] * u[1]; }
             J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
             int o = row_off(N, P.n_cinf, k);
-            visit_rows(P, k, z, up, u, ox(k), oy(k), [&](auto, int r, T c, auto, T, auto, T, T, T, T) {
+            visit_rows<true, W::obca>(P, k, z, up, u, ox(k), oy(k), opsi(k), [&](auto, int r, T c, auto, T, auto, T, auto, T, T, T, T) {
                 T y = fmax(-c, y_min);
                 w.Y(0, o + r) = y;
                 w.S(0, o + r) = mu / y;
@@ -1160,7 +1214,7 @@ struct Solver {
         NodeCtx<T> c;
         c.curv[0] = curv[0]; c.curv[1] = curv[1]; c.curv[2] = curv[2];
         c.uprev[0] = uprev[0]; c.uprev[1] = uprev[1];
-        c.mu = mu; c.alpha = alpha; c.obs = obs; c.x0p = x0p; c.cur = cur; c.second_order = P.second_order; c.ls = ls;
+        c.mu = mu; c.alpha = alpha; c.obs = obs; c.obs_psi = obs_psi; c.x0p = x0p; c.cur = cur; c.second_order = P.second_order; c.ls = ls;
         return c;
     }
 
@@ -1176,7 +1230,7 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < NW; i++) gw[i] = T(0);
 #pragma unroll
-            for (int e = 0; e < NGE; e++) gw[ge_idx(e)] = w.Gw(k, e);
+            for (int e = 0; e < W::nge; e++) gw[ge_idx(e)] = w.Gw(k, e);
             rp = fmax(rp, w.Red(k, 0)); s_max = fmax(s_max, w.Red(k, 1));
             sy_min = fmin(sy_min, w.Red(k, 2)); sy_max = fmax(sy_max, w.Red(k, 3));
             const T ey = w.Z(b, k, IEY), epsi = w.Z(b, k, IEPSI);
@@ -1211,6 +1265,16 @@ struct Solver {
         }
     }
 
+    // The current iterate satisfies the reference's own IPOPT tolerances (mpc.py:133-135: tol = dual_inf_tol =
+    // constr_viol_tol = 1e-3, IPOPT's default compl_inf_tol 1e-4; the primal bound tightened to the north star's 1e-6):
+    // when the solve ends in a failure (iteration cap, regularisation limit, budget of forward passes) at such a point,
+    // it is returned with status 6 instead.  Never pre-empts the tight convergence test.  Residuals are those of
+    // the last adjoint sweep.
+    IGT_HD bool acceptable() const
+    {
+        return P.acc_tol > T(0) && stat <= P.acc_tol * fmax(T(1), s_max) && rp <= P.acc_rp && sy_max <= P.acc_comp;
+    }
+
     // convergence test, exits, barrier update.  Residuals are those of the last adjoint sweep; a
     // regularisation change alone does not alter them, so repeating the test is harmless.
     IGT_HD void test_and_update()
@@ -1219,7 +1283,7 @@ struct Solver {
             status = 0; done = true;
             return;
         }
-        if (iters >= P.max_iter) { status = 1; done = true; return; }
+        if (iters >= P.max_iter) { status = acceptable() ? 6 : 1; done = true; return; }
         if (iters >= P.stall_iter && rp > P.stall_rp) { status = 5; done = true; return; }   // stalled, infeasible
         while (mu > P.mu_floor &&
                fmax(fmax(stat, rp), fmax(fabs(sy_max - mu), fabs(sy_min - mu))) <= P.kappa_eps * mu)
@@ -1240,9 +1304,12 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < 66; i++) H[i] = T(0);
 #pragma unroll
-            for (int e = 0; e < NGE; e++) g[ge_idx(e)] = w.Gl(N, e);
+            for (int e = 0; e < W::nge; e++) g[ge_idx(e)] = w.Gl(N, e);
 #pragma unroll
             for (int e = 0; e < 5; e++) H[sym11(he_i(e), he_j(e))] = w.Hl(N, e);     // terminal rows: ey, collision
+            if (W::obca) {                                                            // ... and the OBCA row's heading entries
+                H[sym11(IPSI, IPSI)] = w.Hl(N, 14); H[sym11(IX, IPSI)] = w.Hl(N, 22); H[sym11(IY, IPSI)] = w.Hl(N, 23);
+            }
 #pragma unroll
             for (int i = 0; i < NA; i++) {
                 Vx[i] = g[i];
@@ -1290,9 +1357,9 @@ struct Solver {
             H[sym11(IEY, IEY)] += T(2); H[sym11(IEPSI, IEPSI)] += T(2);
             H[sym11(IUA, IUA)] += T(2) * P.w_u; H[sym11(IUD, IUD)] += T(2) * P.w_u;
 #pragma unroll
-            for (int e = 0; e < NGE; e++) g[ge_idx(e)] += w.Gl(k, e);
+            for (int e = 0; e < W::nge; e++) g[ge_idx(e)] += w.Gl(k, e);
 #pragma unroll
-            for (int e = 0; e < NHE; e++) H[sym11(he_i(e), he_j(e))] += w.Hl(k, e);
+            for (int e = 0; e < W::nhe; e++) H[sym11(he_i(e), he_j(e))] += w.Hl(k, e);
             T q00 = H[sym11(IUA, IUA)] + reg, q11 = H[sym11(IUD, IUD)] + reg, q01 = H[sym11(IUA, IUD)];
             T det = q00 * q11 - q01 * q01;
             if (!(q00 > T(0) && det > T(1e-12) * q00 * q11)) {
@@ -1359,11 +1426,12 @@ struct Solver {
                 for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dz[j]; d1 += w.KK(k, 1, j) * dz[j]; }
                 dw[IUA] = d0; dw[IUD] = d1;
             }
-            visit_rows<false>(P, k, z, up, u, ox(k), oy(k), [&](auto SL, int, T c, auto I0, T g0, auto I1, T g1, T, T, T) {
-                constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value;
+            visit_rows<false, W::obca>(P, k, z, up, u, ox(k), oy(k), opsi(k), [&](auto SL, int, T c, auto I0, T g0, auto I1, T g1, auto I2, T g2, T, T, T) {
+                constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
                 const T y = yv[sl];
                 T dc = g0 * dw[i0];
                 if constexpr (i1 >= 0) dc += g1 * dw[i1];
+                if constexpr (i2 >= 0) dc += g2 * dw[i2];
                 T dy = -(c + y) - dc;
                 if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
             });
@@ -1416,7 +1484,7 @@ struct Solver {
         for (;;) {
             if (riccati_sweep()) break;
             reg = fmax(fmax(reg * P.reg_up, P.reg_min), reg_hint);
-            if (reg > P.reg_max) { status = 3; done = true; return; }
+            if (reg > P.reg_max) { status = acceptable() ? 6 : 3; done = true; return; }
         }
         need_back = 0;
         ls = 0;
@@ -1444,7 +1512,19 @@ struct Solver {
         trial_ok = w.Tc(nb, 0) != T(0);
         if (!trial_ok) return;
         T th = T(0), lg = T(0), bad = T(0);
+#if !defined(IGT_COLLECT_BATCH)
         for (int k = 0; k <= P.N; k++) { th += w.Tr(nb, k, 0); lg += w.Tr(nb, k, 1); bad += w.Tr(nb, k, 2); }
+#else
+        for (int k0 = 0; k0 <= P.N; k0 += 8) {                   // eight nodes' loads in flight at a time, summed in node order
+            T t8[8][3];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (k0 + i <= P.N) { t8[i][0] = w.Tr(nb, k0 + i, 0); t8[i][1] = w.Tr(nb, k0 + i, 1); t8[i][2] = w.Tr(nb, k0 + i, 2); }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (k0 + i <= P.N) { th += t8[i][0]; lg += t8[i][1]; bad += t8[i][2]; }
+        }
+#endif
         Jcand = w.Tc(nb, 1); thetacand = th; lgcand = lg;
         if (bad > T(0)) trial_ok = false;
     }
@@ -1475,12 +1555,12 @@ struct Solver {
             if (ls >= P.n_alpha) {
                 reg = fmax(reg * P.reg_up, P.reg_min);
                 iters++;
-                if (reg > P.reg_max) { status = 4; done = true; }
+                if (reg > P.reg_max) { status = acceptable() ? 6 : 4; done = true; }
                 need_back = 1;
             }
         }
         // budget of forward passes, checked between iterations like the iteration cap
-        if (!done && (jacc >= 0 || need_back == 1) && trials >= P.max_trials) { status = 1; done = true; }
+        if (!done && (jacc >= 0 || need_back == 1) && trials >= P.max_trials) { status = (jacc < 0 && acceptable()) ? 6 : 1; done = true; }
     }
 
     // judge candidates 0 .. nj-1 in the order sequential halving would try them
@@ -1532,10 +1612,7 @@ struct Solver {
             load_z(b, k, z); load_up(b, k, up);
             for (int i = 0; i < NZ; i++) io.x[(p * (N + 1) + k) * NZ + i] = double(z[i]);
             m = fmax(m, fabs(z[IEY]) - P.ey_lim);
-            if (k >= 1) {
-                T dx = z[IX] - ox(k), dy = z[IY] - oy(k);
-                m = fmax(m, P.d_min * P.d_min - dx * dx - dy * dy);
-            }
+            if (k >= 1) m = fmax(m, collision_row_ref(k, z[IX], z[IY], z[IPSI]));
             if (k < N) {
                 T u[2] = { w.U(b, k, 0), w.U(b, k, 1) };
                 io.u[(p * N + k) * 2] = double(u[0]); io.u[(p * N + k) * 2 + 1] = double(u[1]);
@@ -1558,12 +1635,12 @@ struct Solver {
 
 // Whole solve of problem p in workspace slot `slot`, one thread, start to finish.
 // (tests/hostsim calls this on the CPU; the kernels use the persistent-lane driver below.)
-template <typename T>
+template <typename T, bool OBCA = false>
 IGT_HD void solve_problem(const DevParams<T> &P, const ProbIO &io, T *ws_base, long slot, long p,
                           double *guess_buf, T *mlp_scratch, int mlp_width)
 {
-    Solver<T> sv(P);
-    sv.w.L.init(P.N, P.n_cinf);
+    Solver<T, Ws<T, 32, OBCA>> sv(P);
+    sv.w.init_layout(P.N, P.n_cinf);
     sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
     const double *u_src = io.u_init ? io.u_init + p * P.N * 2 : guess_buf;
@@ -1614,6 +1691,7 @@ __device__ __forceinline__ void term_from_tc(const float *o, TermVal<T> &t)
 constexpr int MAX_SOLVE_BLOCK = IGT_MAX_SOLVE_BLOCK;
 template <typename T>
 struct NodeList {                    // shared-memory work list of one CTA-wide phase
+    int cslot;                       // constant-memory slot of this launch's parameters (ConstP<T>::get)
     int wcnt[MAX_SOLVE_BLOCK / 32];
     int slot[MAX_SOLVE_BLOCK];
     NodeCtx<T> ctx[MAX_SOLVE_BLOCK];
@@ -1646,11 +1724,11 @@ __device__ __forceinline__ int cta_list_build(bool need, long bound, const S &sv
 // which the translation unit defines.
 template <typename T> struct ConstP;
 
-template <typename T, int PHASE, int STRIDE>
+template <typename T, int PHASE, int STRIDE, bool OBCA>
 __device__ __noinline__ void phase_items(T *ws_base, const NodeList<T> *nl, int n, int n_spec)
 {
-    const DevParams<T> &P = ConstP<T>::get();
-    Ws<T, STRIDE> w; w.L.init(P.N, P.n_cinf);
+    const DevParams<T> &P = ConstP<T>::get(nl->cslot);
+    Ws<T, STRIDE, OBCA> w; w.init_layout(P.N, P.n_cinf);
     if (PHASE == 1 || PHASE == 2) {
         const int total = n * (P.N + 1);
         for (int it = threadIdx.x; it < total; it += blockDim.x) {
@@ -1678,7 +1756,7 @@ __device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base
                                                long bound, const S &sv, NodeList<T> &nl)
 {
     const int n = cta_list_build(need, bound, sv, nl);
-    if (n > 0) phase_items<T, PHASE, STRIDE>(ws_base, &nl, n, 1);
+    if (n > 0) phase_items<T, PHASE, STRIDE, S::obca>(ws_base, &nl, n, 1);
     __syncthreads();
 }
 
@@ -1695,6 +1773,9 @@ __device__ long long g_mid_t;            // debug: end of the rollouts of CTA 0'
 // threads roll out the next halvings at the same time, each into its own iterate buffer, and the
 // owner then takes the first candidate that passes -- the same iterate sequential halving reaches,
 // in one pass instead of up to n_alpha.  Returns the number of candidates per problem.
+#ifndef IGT_SPEC_BUDGET
+#define IGT_SPEC_BUDGET IGT_MAX_SOLVE_BLOCK
+#endif
 template <typename T, int STRIDE, typename S>
 __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
                                                long bound, const S &sv, NodeList<T> &nl, bool speculate, int &n_out)
@@ -1702,12 +1783,13 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
     const int n = cta_list_build(need, bound, sv, nl);
     n_out = n;
     if (n == 0) { IGT_MID_TICK(); return 1; }                     // CTA-uniform
+    // IGT_SPEC_BUDGET: most candidates (problems x halvings) evaluated at once; the default fills the CTA's threads
     int n_spec = 1;
-    if (speculate) { n_spec = (int)blockDim.x / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
-    phase_items<T, 3, STRIDE>(ws_base, &nl, n, n_spec);
+    if (speculate) { n_spec = IGT_SPEC_BUDGET / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
+    phase_items<T, 3, STRIDE, S::obca>(ws_base, &nl, n, n_spec);
     __syncthreads();
     IGT_MID_TICK();
-    phase_items<T, 4, STRIDE>(ws_base, &nl, n, n_spec);
+    phase_items<T, 4, STRIDE, S::obca>(ws_base, &nl, n, n_spec);
     __syncthreads();
     return n_spec;
 }
@@ -1758,15 +1840,16 @@ __device__ int g_round_ph[512][12];      // per loop pass: kcycles per phase
 #define IGT_TICK(i) do { } while (0)
 #endif
 
-template <typename T, bool TC, int STRIDE = 32>
+template <typename T, bool TC, int STRIDE = 32, bool OBCA = false>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
                                                  long slot, long B, const Sched &sc,
                                                  const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc,
-                                                 int quota)
+                                                 int quota, int cslot)
 {
     __shared__ NodeList<T> nl;
-    Solver<T, Ws<T, STRIDE>> sv(P);
-    sv.w.L.init(P.N, P.n_cinf);
+    if (threadIdx.x == 0) nl.cslot = cslot;                     // (the first CTA barrier of the loop publishes it)
+    Solver<T, Ws<T, STRIDE, OBCA>> sv(P);
+    sv.w.init_layout(P.N, P.n_cinf);
     sv.w.bind(ws_base, slot);
     sv.mlp_scratch = mlp_scratch; sv.mlp_width = mlp_width;
     const unsigned FULL = 0xffffffffu;
@@ -1838,7 +1921,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
             for (;;) {
                 if (sv.riccati_sweep()) break;
                 sv.reg = fmax(fmax(sv.reg * P.reg_up, P.reg_min), sv.reg_hint);
-                if (sv.reg > P.reg_max) { sv.status = 3; sv.done = true; break; }
+                if (sv.reg > P.reg_max) { sv.status = sv.acceptable() ? 6 : 3; sv.done = true; break; }
             }
             IGT_TICK(4);
             if (!sv.done) { sv.need_back = 0; sv.ls = 0; sv.step_bound(); }

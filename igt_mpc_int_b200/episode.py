@@ -22,6 +22,8 @@ import time
 
 import numpy as np
 
+from . import _lib
+
 from . import geometry as G
 
 A_MIN_BRAKE = -4.0     # mpc.yaml:8 a_min, evaluate.py:516
@@ -157,7 +159,7 @@ def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_la
             out["x"][idx], out["u"][idx], out["status"][idx] = r["x"], r["u"], r["status"]
         if record_latency:
             lat.append(1e3 * (time.perf_counter() - t0))
-        ok = out["status"] == 0
+        ok = np.isin(out["status"], _lib.STATUS_OK)        # converged or within the reference's own tolerances
         # ---- plant update ----
         z_next = z.copy(); u_app = np.zeros((B, 2))
         z_next[ok] = out["x"][ok, 1]                                                       # evaluate.py:493

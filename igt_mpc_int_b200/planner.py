@@ -133,8 +133,9 @@ class BatchSolver:
         return out
 
     # -- host-pointer calls (copies inside) ---------------------------------------------------
-    def solve_batch(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None, out=None):
-        """numpy in / numpy out.  Returns dict(x[B,N+1,7], u[B,N,2], cost, viol, status, iters)."""
+    def solve_batch(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None, out=None, obs_psi=None):
+        """numpy in / numpy out.  Returns dict(x[B,N+1,7], u[B,N,2], cost, viol, status, iters).
+        obs_psi[B,N+1] (obstacle heading forecast) selects the OBCA collision rows (mpc.py:211-221)."""
         N = self.N
         x0 = _f64(x0)
         B = x0.shape[0]
@@ -142,16 +143,17 @@ class BatchSolver:
         obs_xy = _f64(obs_xy, (B, N + 1, 2))
         nn_ctx = None if nn_ctx is None else _f64(nn_ctx, (B, 4))
         u_init = None if u_init is None else _f64(u_init, (B, N, 2))
+        obs_psi = None if obs_psi is None else _f64(obs_psi, (B, N + 1))
         if out is None:
             out = dict(x=np.empty((B, N + 1, 7)), u=np.empty((B, N, 2)), cost=np.empty(B), viol=np.empty(B),
                        status=np.empty(B, dtype=np.int32), iters=np.empty(B, dtype=np.int32))
-        rc = self.lib.igt_solve_host(self._h, B, _hp(x0), _hp(u_prev), _hp(curv), _hp(obs_xy), _hp(nn_ctx),
+        rc = self.lib.igt_solve_host(self._h, B, _hp(x0), _hp(u_prev), _hp(curv), _hp(obs_xy), _hp(obs_psi), _hp(nn_ctx),
                                      _hp(u_init), _hp(out["x"]), _hp(out["u"]), _hp(out["cost"]),
                                      _hp(out["viol"]), _hp(out["status"]), _hp(out["iters"]))
         self._check(rc, "igt_solve_host")
         return out
 
-    def evaluate(self, x0, u_prev, curv, obs_xy, u, nn_ctx=None):
+    def evaluate(self, x0, u_prev, curv, obs_xy, u, nn_ctx=None, obs_psi=None):
         """Cost (mpc.py:356-373) and max inequality-row value of given controls."""
         N = self.N
         x0 = _f64(x0)
@@ -159,8 +161,9 @@ class BatchSolver:
         u_prev = _f64(u_prev, (B, 2)); curv = _f64(curv, (B, 3)); obs_xy = _f64(obs_xy, (B, N + 1, 2))
         u = _f64(u, (B, N, 2))
         nn_ctx = None if nn_ctx is None else _f64(nn_ctx, (B, 4))
+        obs_psi = None if obs_psi is None else _f64(obs_psi, (B, N + 1))
         cost, viol, z = np.empty(B), np.empty(B), np.empty((B, N + 1, 7))
-        rc = self.lib.igt_eval_host(self._h, B, _hp(x0), _hp(u_prev), _hp(curv), _hp(obs_xy), _hp(nn_ctx),
+        rc = self.lib.igt_eval_host(self._h, B, _hp(x0), _hp(u_prev), _hp(curv), _hp(obs_xy), _hp(obs_psi), _hp(nn_ctx),
                                     _hp(u), _hp(cost), _hp(viol), _hp(z))
         self._check(rc, "igt_eval_host")
         return dict(cost=cost, viol=viol, x=z)
@@ -184,15 +187,22 @@ class BatchSolver:
         return (z, A, Bm) if jac else z
 
     # -- device-pointer call (torch tensors already in HBM; no copies, no sync) ---------------
-    def solve_batch_device(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None, out=None, stream=None):
+    def solve_batch_device(self, x0, u_prev, curv, obs_xy, nn_ctx=None, u_init=None, out=None, stream=None, obs_psi=None):
         """torch CUDA float64 tensors in / out; enqueues on the current torch stream."""
         import torch
         N = self.N
         B = x0.shape[0]
-        for t, shp in ((x0, (B, 7)), (u_prev, (B, 2)), (curv, (B, 3)), (obs_xy, (B, N + 1, 2))):
-            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == shp):
-                raise ValueError("expected contiguous CUDA float64 tensor of shape %s" % (shp,))
         dev = x0.device
+
+        def check(t, shp, dtype, name):
+            if not (t.is_cuda and t.device == dev and t.dtype == dtype and t.is_contiguous() and tuple(t.shape) == shp):
+                raise ValueError("%s: expected a contiguous %s tensor of shape %s on %s" % (name, dtype, shp, dev))
+
+        for t, shp, name in ((x0, (B, 7), "x0"), (u_prev, (B, 2), "u_prev"), (curv, (B, 3), "curv"),
+                             (obs_xy, (B, N + 1, 2), "obs_xy"), (nn_ctx, (B, 4), "nn_ctx"), (u_init, (B, N, 2), "u_init"),
+                             (obs_psi, (B, N + 1), "obs_psi")):
+            if t is not None:
+                check(t, shp, torch.float64, name)
         if out is None:
             out = dict(x=torch.empty((B, N + 1, 7), dtype=torch.float64, device=dev),
                        u=torch.empty((B, N, 2), dtype=torch.float64, device=dev),
@@ -200,9 +210,13 @@ class BatchSolver:
                        viol=torch.empty(B, dtype=torch.float64, device=dev),
                        status=torch.empty(B, dtype=torch.int32, device=dev),
                        iters=torch.empty(B, dtype=torch.int32, device=dev))
+        else:
+            for k, shp, dt in (("x", (B, N + 1, 7), torch.float64), ("u", (B, N, 2), torch.float64), ("cost", (B,), torch.float64),
+                               ("viol", (B,), torch.float64), ("status", (B,), torch.int32), ("iters", (B,), torch.int32)):
+                check(out[k], shp, dt, "out[%r]" % k)
         st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
         p = lambda t: None if t is None else _vp(t.data_ptr())
-        rc = self.lib.igt_solve_dev(self._h, B, p(x0), p(u_prev), p(curv), p(obs_xy), p(nn_ctx), p(u_init),
+        rc = self.lib.igt_solve_dev(self._h, B, p(x0), p(u_prev), p(curv), p(obs_xy), p(obs_psi), p(nn_ctx), p(u_init),
                                     p(out["x"]), p(out["u"]), p(out["cost"]), p(out["viol"]), p(out["status"]),
                                     p(out["iters"]), _vp(st))
         self._check(rc, "igt_solve_dev")
@@ -217,7 +231,7 @@ class _Sol:
     def __init__(self, t_wall, iters, status):
         self._stats = {"t_wall_total": t_wall, "t_proc_total": t_wall, "iter_count": int(iters),
                        "return_status": _lib.STATUS_NAMES.get(int(status), "unknown"),
-                       "success": int(status) == 0}
+                       "success": int(status) in _lib.STATUS_OK}
 
     def stats(self):
         return dict(self._stats)
@@ -238,11 +252,11 @@ class MPC_Planner:
                  precision="f64", **options):
         assert index is not None                                        # mpc.py:80
         assert agents is not None, 'Agents are not defined'             # mpc.py:155
-        if ca_type != 'circle':
-            raise NotImplementedError("only collision_avoidance_type 'circle' (mpc.yaml:16) is on the GPU path")
+        if ca_type not in ('circle', 'obca'):
+            raise ValueError("collision_avoidance_type must be 'circle' or 'obca' (mpc.yaml:15-16)")
         self.N, self.dt, self.ca_type = N, dt, ca_type
         self.x_sol_prev = None
-        self.d_min = 2 * ca_radius                                      # mpc.py:45
+        self.d_min = 0 if ca_type == 'obca' else 2 * ca_radius          # mpc.py:42-45
         self.routes, self.ind = routes, index
         self.agents, self.goals, self.ref = agents, goals, ref
         self.initial_agent = agents[index]
@@ -267,6 +281,7 @@ class MPC_Planner:
                              "reference unpickles them from a dataset that is not shipped (mpc.py:105-118)")
         self._x0 = np.zeros((1, 7)); self._uprev = np.zeros((1, 2))
         self._obs = np.full((1, N + 1, 2), -20.0); self._ctx = np.zeros((1, 4))
+        self._obs_psi = np.zeros((1, N + 1))                            # obstacle heading forecast (OBCA rows only)
 
     # mpc.py:183-200 -- curvature of this agent's route as (b0, b1, Kval)
     def _curvature_params(self):
@@ -299,8 +314,11 @@ class MPC_Planner:
             if i != self.ind:
                 self.pred_ind.append(i)
                 assert len(pred) == self.N + 1, ValueError('Invalid prediction length (Horizon)')
+                flip = self.routes[i] in ['32', '41']                   # mpc.py:250-253
                 for k in range(self.N + 1):
                     self._obs[0, k] = (pred[k].x, pred[k].y)
+                    if self.ca_type == 'obca':
+                        self._obs_psi[0, k] = abs(pred[k].heading) if flip else pred[k].heading
         if raw_preds is not None:
             j = self.pred_ind[0]
             enc = G.scenario_encoding(self.routes)
@@ -313,10 +331,11 @@ class MPC_Planner:
             u_init = None if u_sol_prev is None else np.ascontiguousarray(np.asarray(u_sol_prev, dtype=np.float64).T)[None]
             t0 = time.time()
             out = self._solver.solve_batch(self._x0, self._uprev, self.curv, self._obs,
-                                           nn_ctx=self._ctx if self.use_NN_cost2go else None, u_init=u_init)
+                                           nn_ctx=self._ctx if self.use_NN_cost2go else None, u_init=u_init,
+                                           obs_psi=self._obs_psi if self.ca_type == 'obca' else None)
             self.solve_time = time.time() - t0
             self.sol = _Sol(self.solve_time, out["iters"][0], out["status"][0])
-            if int(out["status"][0]) != 0:
+            if int(out["status"][0]) not in _lib.STATUS_OK:   # IPOPT: Solve_Succeeded covers both (igt_mpc.h)
                 raise RuntimeError(_lib.STATUS_NAMES.get(int(out["status"][0]), "failed"))
             x = np.ascontiguousarray(out["x"][0].T)       # [7, N+1]
             u = np.ascontiguousarray(out["u"][0].T)       # [2, N]

@@ -28,13 +28,15 @@ class ProblemBatch:
     nn_ctx: np.ndarray    # [B, 4]  (s_tv, v_tv, e_tv, e_ego)        mpc.py:326-337
     scenario: np.ndarray  # [B] int32 scenario 1..8
     route: list           # [B] ego route string
+    obs_psi: np.ndarray = None   # [B, N+1] other vehicle's heading forecast (OBCA rows, mpc.py:211-221); mid_episode only
 
     def __len__(self):
         return self.x0.shape[0]
 
     def slice(self, lo, hi):
         return ProblemBatch(self.x0[lo:hi], self.u_prev[lo:hi], self.curv[lo:hi], self.obs[lo:hi],
-                            self.nn_ctx[lo:hi], self.scenario[lo:hi], self.route[lo:hi])
+                            self.nn_ctx[lo:hi], self.scenario[lo:hi], self.route[lo:hi],
+                            None if self.obs_psi is None else self.obs_psi[lo:hi])
 
 
 def _route_xy(s, route):
@@ -79,6 +81,7 @@ def mid_episode(B, N=40, scenarios=(1, 2, 3, 4, 5, 6, 7, 8), seed=2026, dt=0.1, 
     assert per * len(scenarios) == B, "B must be a multiple of the number of scenarios"
     x0 = np.empty((B, 7)); up = np.empty((B, 2)); curv = np.empty((B, 3))
     obs = np.empty((B, N + 1, 2)); ctx = np.empty((B, 4)); scen = np.empty(B, dtype=np.int32)
+    obs_psi = np.zeros((B, N + 1))
     routes_out = []
     i = 0
     for sc in scenarios:
@@ -103,12 +106,15 @@ def mid_episode(B, N=40, scenarios=(1, 2, 3, 4, 5, 6, 7, 8), seed=2026, dt=0.1, 
             up[i] = (ap[ego], dp[ego])
             curv[i] = G.curvature_params(routes[ego])
             obs[i] = G.filter_obstacle((xe, ye), psi, fc[:, :2])
+            if obs[i, 0, 0] != -20.0:                                # heading of the forecast poses (mpc.py:250-260: abs() on 32 / 41)
+                hd = np.array([G.frenet2global(fc[k, 2], routes[oth])[2] for k in range(N + 1)])
+                obs_psi[i] = np.abs(hd) if routes[oth] in ('32', '41') else hd
             ctx[i] = (fc[N, 2], fc[N, 3], enc[oth], enc[ego])
             scen[i] = sc
             routes_out.append(routes[ego])
             i += 1
             n_done += 1
-    return ProblemBatch(x0, up, curv, obs, ctx, scen, routes_out)
+    return ProblemBatch(x0, up, curv, obs, ctx, scen, routes_out, obs_psi)
 
 
 def episode_start(B, N=40, scenarios=(1, 2, 3, 4, 5, 6, 7, 8), seed=2026, dt=0.1):

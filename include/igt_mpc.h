@@ -13,6 +13,13 @@
  * Every function returns 0 on success or a negative IGT_E* code; igt_last_error() gives text.
  * No C++ exception crosses this boundary.
  *
+ * Concurrency.  Different handles are independent: they may be used from different host threads and on different
+ * streams at the same time, whatever their horizons, limits or value networks (each handle keeps its parameters
+ * in its own constant-memory slot and owns its workspace).  Calls on ONE handle may come from any thread and any
+ * stream, but they are serialised: a per-handle mutex on the host, and on the device every call waits (stream
+ * event) for the handle's previous call before it touches the handle's workspace.  `*_dev` calls never block the
+ * host: buffers grow with the stream-ordered allocator.  Each call selects the handle's device (cudaSetDevice).
+ *
  * Layouts (reference mpc.py:163-164):  state z = [x, y, s, ey, epsi, v, psi], input u = [a, df].
  */
 #ifndef IGT_MPC_H
@@ -38,6 +45,8 @@ extern "C" {
 #define IGT_STATUS_REG_LIMIT 3
 #define IGT_STATUS_LINESEARCH 4
 #define IGT_STATUS_STALLED 5         /* still infeasible (|c + slack| > stall_rp) after stall_iter iterations */
+#define IGT_STATUS_ACCEPTABLE 6      /* failed to converge tightly, but the final point is within the reference's IPOPT tolerances (see acc_tol):
+                                        a success for the host (IPOPT returns Solve_Succeeded there), reported apart */
 
 #define IGT_PREC_F32 0
 #define IGT_PREC_F64 1
@@ -79,6 +88,16 @@ typedef struct {
                           giving up early on problems that burn all n_alpha halvings iteration after iteration
                           (the reference's counterpart is IPOPT's max_wall_time, mpc.py:139); 0 = no budget (default) */
     int precision;     /* IGT_PREC_F32 / IGT_PREC_F64: arithmetic of the solver kernels */
+    /* Reference-tolerance exit -> IGT_STATUS_ACCEPTABLE.  When a solve ends in a failure (the iteration cap, the
+     * regularisation limit, the budget of forward passes) at a point that already
+     * satisfies the reference's own IPOPT tolerances (mpc.py:133-135: tol = dual_inf_tol = constr_viol_tol = 1e-3;
+     * IPOPT's default compl_inf_tol = 1e-4), the point is returned as acceptable instead of failed -- IPOPT itself
+     * would have stopped there with Solve_Succeeded.  stationarity <= acc_tol * max(1, |mult|_inf), primal residual
+     * <= acc_rp (default 1e-6: the north star's violation bound, not the reference's 1e-3), max(mult * slack) <=
+     * acc_comp.  acc_tol = 0 disables. */
+    double acc_tol, acc_rp, acc_comp;
+    double x0_tol;     /* tolerance of the rows that involve x0 only (IGT_STATUS_X0_INFEASIBLE); default 1e-6, so that the
+                          x[:,1] of a converged plan (rows met to tol_rp) is a valid x0 of the next closed-loop step */
 } igt_params;
 
 /* Fill `p` with the reference's effective constants (N=40, dt=0.1, n_rk=4, limits of
@@ -115,25 +134,29 @@ int igt_rollout_host(igt_handle *h, int B, const float *z0, const float *u, cons
 /* Cost (mpc.py:356-373) and the largest inequality-row value, rows exactly as written in
  * mpc.py:177-180,:223-226,:296-321 (collision in squared-distance units), of given controls.
  * The state trajectory is re-rolled on the device.  fp64 arrays: x0[B,7], u_prev[B,2],
- * curv[B,3], obs_xy[B,N+1,2], nn_ctx[B,4] = (s_tv, v_tv, e_tv, e_ego) or NULL ('mpc' cost),
- * u[B,N,2] -> cost[B], viol[B], z[B,N+1,7] (z may be NULL). */
+ * curv[B,3], obs_xy[B,N+1,2], obs_psi[B,N+1] or NULL (see igt_solve_*), nn_ctx[B,4] = (s_tv, v_tv, e_tv, e_ego) or
+ * NULL ('mpc' cost), u[B,N,2] -> cost[B], viol[B], z[B,N+1,7] (z may be NULL). */
 int igt_eval_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
-                  const double *obs_xy, const double *nn_ctx, const double *u, double *cost,
-                  double *viol, double *z);
+                  const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u,
+                  double *cost, double *viol, double *z);
 
 /* Replaces MPC_Planner.update_initial_condition / update_predictions / solve
  * (mpc.py:280-294, :241-278, :383-406) for a batch of independent problems.
  * In : x0[B,7]; u_prev[B,2]; curv[B,3]; obs_xy[B,N+1,2] (row 0 unused, mpc.py:224);
+ *      obs_psi[B,N+1] or NULL -- non-NULL selects collision_avoidance_type 'obca' (mpc.py:42-43, :170-175, :211-221):
+ *      the obstacle's heading forecast (preds row 6, mpc.py:250-260); the rows are enforced in dual-eliminated
+ *      form, margin 1e-6 + d_min - signed distance between the two 4.47 x 2.0 rectangles <= 0 (csrc/obca.cuh), with
+ *      d_min = 0 as the reference sets it for this mode; viol[] then reports that row.  f64 only.
  *      nn_ctx[B,4] or NULL -- non-NULL selects the gt_mpc terminal cost (mpc.py:367-369);
  *      u_init[B,N,2] or NULL -- warm start (mpc.py:386-389); NULL = cold-start rule.
  * Out: x[B,N+1,7], u[B,N,2], cost[B], viol[B] (max inequality row, reference units),
  *      status[B] (IGT_STATUS_*), iters[B].  All fp64 / int32. */
 int igt_solve_dev(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
-                  const double *obs_xy, const double *nn_ctx, const double *u_init, double *x,
-                  double *u, double *cost, double *viol, int *status, int *iters, void *stream);
+                  const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u_init,
+                  double *x, double *u, double *cost, double *viol, int *status, int *iters, void *stream);
 int igt_solve_host(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
-                   const double *obs_xy, const double *nn_ctx, const double *u_init, double *x,
-                   double *u, double *cost, double *viol, int *status, int *iters);
+                   const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u_init,
+                   double *x, double *u, double *cost, double *viol, int *status, int *iters);
 
 /* Number of kernels this library has launched on `h` so far (bench.py's gpu_launches). */
 long long igt_launch_count(const igt_handle *h);

@@ -33,6 +33,7 @@ class CParams(C.Structure):
         ("alpha_safety", C.c_double),
         ("reg_jump", C.c_double),
         ("stall_iter", C.c_int), ("stall_rp", C.c_double),
+        ("acc_tol", C.c_double), ("acc_rp", C.c_double), ("acc_comp", C.c_double),
         ("n_layers", C.c_int), ("dims", C.c_int * (MAX_LAYERS + 1)),
         ("W", _dp * MAX_LAYERS), ("b", _dp * MAX_LAYERS),
         ("Wn", C.c_double * 36), ("mu_f", C.c_double * 6), ("sigma_t", C.c_double), ("mu_t", C.c_double),
@@ -134,17 +135,34 @@ class COracle:
         self.lib.igt_oracle_initial_guess(C.byref(self.cp), B, _ptr(x0), _ptr(u_prev), _ptr(curv), _ptr(obs), _ptr(U))
         return U
 
-    def solve(self, x0, u_prev, curv, obs, nn_ctx=None, u_init=None, n_threads=0):
-        x0, u_prev, curv, obs, nn_ctx, u_init = map(_c, (x0, u_prev, curv, obs, nn_ctx, u_init))
+    def solve(self, x0, u_prev, curv, obs, nn_ctx=None, u_init=None, n_threads=0, obs_psi=None):
+        """obs_psi[B,N+1] (obstacle heading forecast) selects the OBCA collision rows (mpc.py:211-221, d_min = 0:
+        build the oracle with nlp.Params(d_min=0.0))."""
+        x0, u_prev, curv, obs, nn_ctx, u_init, obs_psi = map(_c, (x0, u_prev, curv, obs, nn_ctx, u_init, obs_psi))
         B, N = x0.shape[0], self.P.N
-        assert obs.shape == (B, N + 1, 2)
+        assert obs.shape == (B, N + 1, 2) and (obs_psi is None or obs_psi.shape == (B, N + 1))
         if self.cp.n_layers > 0:
             assert nn_ctx is not None
         Z = np.empty((B, N + 1, 7)); U = np.empty((B, N, 2))
         cost, viol = np.empty(B), np.empty(B)
         status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
-        self.lib.igt_oracle_solve_batch(C.byref(self.cp), B, _ptr(x0), _ptr(u_prev), _ptr(curv), _ptr(obs),
+        self.lib.igt_oracle_solve_batch_obca(C.byref(self.cp), B, _ptr(x0), _ptr(u_prev), _ptr(curv), _ptr(obs), _ptr(obs_psi),
                                         _ptr(nn_ctx), _ptr(u_init), _ptr(Z), _ptr(U), _ptr(cost), _ptr(viol),
                                         status.ctypes.data_as(C.POINTER(C.c_int)),
                                         iters.ctypes.data_as(C.POINTER(C.c_int)), n_threads)
         return dict(Z=Z, U=U, cost=cost, viol=viol, status=status, iters=iters)
+
+    def viol_obca(self, x0, u_prev, curv, obs, obs_psi, Z, U):
+        x0, u_prev, curv, obs, obs_psi, Z, U = map(_c, (x0, u_prev, curv, obs, obs_psi, Z, U))
+        viol = np.empty(x0.shape[0])
+        self.lib.igt_oracle_viol_obca(C.byref(self.cp), x0.shape[0], _ptr(x0), _ptr(u_prev), _ptr(curv), _ptr(obs), _ptr(obs_psi),
+                                      _ptr(Z), _ptr(U), _ptr(viol))
+        return viol
+
+
+def rect_sdist(ego, obs):
+    """C port of oracle/obca.rect_distance for n pose pairs: d[n], g[n,3]"""
+    ego, obs = _c(ego), _c(obs)
+    d = np.empty(ego.shape[0]); g = np.empty((ego.shape[0], 3))
+    lib().igt_oracle_rect_sdist(ego.shape[0], _ptr(ego), _ptr(obs), _ptr(d), _ptr(g))
+    return d, g

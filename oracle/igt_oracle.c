@@ -47,7 +47,12 @@ typedef struct {
     int max_ls_fail, max_trials, predict_alpha;
     double alpha_safety;
     double reg_jump;                   /* after a non-PD Quu: reg >= reg_jump * (-lambda_min(Quu)) of that stage */
-    int stall_iter; double stall_rp;   /* local-infeasibility exit: it >= stall_iter and |c + y|_inf > stall_rp -> status 5 */   /* give up after this many consecutive failed line searches / total forward passes */
+    int stall_iter; double stall_rp;   /* local-infeasibility exit: it >= stall_iter and |c + y|_inf > stall_rp -> status 5 */
+    /* reference-tolerance exit (status 6): when the solve ends in a failure (iteration cap, regularisation limit,
+     * budget of forward passes) at a point that already satisfies the reference's own IPOPT tolerances
+     * (mpc.py:133-135: tol = dual_inf_tol = constr_viol_tol = 1e-3; IPOPT's default compl_inf_tol 1e-4) -- with the
+     * primal bound tightened to the north star's 1e-6 -- the point is returned as "acceptable"; acc_tol = 0 disables */
+    double acc_tol, acc_rp, acc_comp;
     /* gt_mpc value term (mpc.py:326-354,:367-369; model.py:14-67); n_layers = 0 -> 'mpc' mode */
     int n_layers;
     int dims[MAX_MLP_LAYERS + 1];
@@ -243,14 +248,15 @@ static void mlp_value(const igt_oracle_params *P, double sN, double vN, const do
 /* ------------------------------------------------------------------ NLP rows ---------- */
 typedef struct {
     double c;            /* row value, c <= 0 feasible */
-    int i0, i1;          /* indices into w = (zeta[9], u[2]); i1 < 0 if single */
-    double g0, g1;       /* gradient entries */
+    int i0, i1, i2;      /* indices into w = (zeta[9], u[2]); i1 / i2 < 0 if unused (i2: heading entry of the OBCA row) */
+    double g0, g1, g2;   /* gradient entries */
     int has_h;           /* collision row: 2x2 Hessian block on (x, y) */
     double hxx, hxy, hyy;
 } row_t;
 
 typedef struct {
     const double *x0, *u_prev, *curv, *obs, *ctx, *u_init;
+    const double *obs_psi;   /* [N+1] obstacle heading forecast -> OBCA collision rows (mpc.py:211-221); NULL -> circle */
 } prob_t;
 
 static inline int n_rows_stage(const igt_oracle_params *P, int k)
@@ -261,11 +267,118 @@ static inline int n_rows_stage(const igt_oracle_params *P, int k)
 
 static inline void set_row(row_t *r, double c, int i0, double g0, int i1, double g1)
 {
-    r->c = c; r->i0 = i0; r->g0 = g0; r->i1 = i1; r->g1 = g1; r->has_h = 0;
+    r->c = c; r->i0 = i0; r->g0 = g0; r->i1 = i1; r->g1 = g1; r->i2 = -1; r->g2 = 0.0; r->has_h = 0;
 }
 
-static void collision_row(const igt_oracle_params *P, const double *z, const double *o, row_t *r)
-{   /* mpc.py:226 in the equivalent distance form d_min - |p - o| <= 0 */
+/* ---- OBCA rows in dual-eliminated form (oracle/obca.py restated in C; pinned there against the reference's
+ * explicit-dual formulation, tests/test_oracle_obca.py): signed distance between two 4.47 x 2.0 rectangles ---- */
+#define OBCA_MARGIN 1e-6   /* mpc.py:216 */
+#define VEH_HL (4.47 / 2)
+#define VEH_HW (2.0 / 2)
+static double sgn1(double v) { return v >= 0 ? 1.0 : -1.0; }
+
+static double point_to_rect(const double q[2], const double pose[3], double cl_local[2], double cl_world[2], int *inside)
+{
+    double c = cos(pose[2]), s = sin(pose[2]);
+    double dx = c * (q[0] - pose[0]) + s * (q[1] - pose[1]), dy = -s * (q[0] - pose[0]) + c * (q[1] - pose[1]);
+    cl_local[0] = fmin(fmax(dx, -VEH_HL), VEH_HL); cl_local[1] = fmin(fmax(dy, -VEH_HW), VEH_HW);
+    *inside = fabs(dx) <= VEH_HL && fabs(dy) <= VEH_HW;
+    cl_world[0] = pose[0] + c * cl_local[0] - s * cl_local[1];
+    cl_world[1] = pose[1] + s * cl_local[0] + c * cl_local[1];
+    return hypot(dx - cl_local[0], dy - cl_local[1]);
+}
+
+static double rect_penetration(const double ego[3], const double obs[3], double g[3])
+{   /* separating-axis test over the four face normals: minus the smallest overlap, gradient w.r.t. the ego pose */
+    double uxe[2] = { cos(ego[2]), sin(ego[2]) }, uye[2] = { -uxe[1], uxe[0] };
+    double uxo[2] = { cos(obs[2]), sin(obs[2]) }, uyo[2] = { -uxo[1], uxo[0] };
+    double dv[2] = { ego[0] - obs[0], ego[1] - obs[1] };
+    double best = 1e300, bg[3] = { 0, 0, 0 };
+    for (int f = 0; f < 2; f++) {
+        const double *a = f == 0 ? uxe : uye;
+        double da[2] = { f == 0 ? uye[0] : -uxe[0], f == 0 ? uye[1] : -uxe[1] }, he = f == 0 ? VEH_HL : VEH_HW;
+        double axo = a[0] * uxo[0] + a[1] * uxo[1], ayo = a[0] * uyo[0] + a[1] * uyo[1], ad = a[0] * dv[0] + a[1] * dv[1];
+        double ov = he + VEH_HL * fabs(axo) + VEH_HW * fabs(ayo) - fabs(ad);
+        if (ov < best) {
+            best = ov; bg[0] = -sgn1(ad) * a[0]; bg[1] = -sgn1(ad) * a[1];
+            bg[2] = VEH_HL * sgn1(axo) * (da[0] * uxo[0] + da[1] * uxo[1]) + VEH_HW * sgn1(ayo) * (da[0] * uyo[0] + da[1] * uyo[1])
+                    - sgn1(ad) * (da[0] * dv[0] + da[1] * dv[1]);
+        }
+    }
+    for (int f = 0; f < 2; f++) {
+        const double *a = f == 0 ? uxo : uyo;
+        double ho = f == 0 ? VEH_HL : VEH_HW;
+        double axe = a[0] * uxe[0] + a[1] * uxe[1], aye = a[0] * uye[0] + a[1] * uye[1], ad = a[0] * dv[0] + a[1] * dv[1];
+        double ov = VEH_HL * fabs(axe) + VEH_HW * fabs(aye) + ho - fabs(ad);
+        if (ov < best) {
+            best = ov; bg[0] = -sgn1(ad) * a[0]; bg[1] = -sgn1(ad) * a[1];
+            bg[2] = VEH_HL * sgn1(axe) * aye + VEH_HW * sgn1(aye) * (-axe);
+        }
+    }
+    g[0] = -bg[0]; g[1] = -bg[1]; g[2] = -bg[2];
+    return -best;
+}
+
+static double rect_signed_distance(const double ego[3], const double obs[3], double g[3])
+{
+    static const double loc[4][2] = { { VEH_HL, VEH_HW }, { -VEH_HL, VEH_HW }, { -VEH_HL, -VEH_HW }, { VEH_HL, -VEH_HW } };
+    double Pe[4][2], Po[4][2];
+    double ce = cos(ego[2]), se = sin(ego[2]), co = cos(obs[2]), so = sin(obs[2]);
+    for (int i = 0; i < 4; i++) {
+        Pe[i][0] = ego[0] + ce * loc[i][0] - se * loc[i][1]; Pe[i][1] = ego[1] + se * loc[i][0] + ce * loc[i][1];
+        Po[i][0] = obs[0] + co * loc[i][0] - so * loc[i][1]; Po[i][1] = obs[1] + so * loc[i][0] + co * loc[i][1];
+    }
+    double best = 1e300, a[2] = { 0, 0 }, b[2] = { 0, 0 }, al[2] = { 0, 0 };
+    for (int i = 0; i < 4; i++) {
+        double cl[2], cw[2]; int in;
+        double d = point_to_rect(Pe[i], obs, cl, cw, &in);
+        if (in) return rect_penetration(ego, obs, g);
+        if (d < best) { best = d; a[0] = Pe[i][0]; a[1] = Pe[i][1]; b[0] = cw[0]; b[1] = cw[1]; al[0] = loc[i][0]; al[1] = loc[i][1]; }
+    }
+    for (int j = 0; j < 4; j++) {
+        double cl[2], cw[2]; int in;
+        double d = point_to_rect(Po[j], ego, cl, cw, &in);
+        if (in) return rect_penetration(ego, obs, g);
+        if (d < best) { best = d; a[0] = cw[0]; a[1] = cw[1]; b[0] = Po[j][0]; b[1] = Po[j][1]; al[0] = cl[0]; al[1] = cl[1]; }
+    }
+    for (int i = 0; i < 4; i++)                                   /* crossing edges without a vertex inside */
+        for (int j = 0; j < 4; j++) {
+            double d1x = Pe[(i + 1) & 3][0] - Pe[i][0], d1y = Pe[(i + 1) & 3][1] - Pe[i][1];
+            double d2x = Po[(j + 1) & 3][0] - Po[j][0], d2y = Po[(j + 1) & 3][1] - Po[j][1];
+            double den = d1x * d2y - d1y * d2x;
+            if (fabs(den) < 1e-14) continue;
+            double rx = Po[j][0] - Pe[i][0], ry = Po[j][1] - Pe[i][1];
+            double t = (rx * d2y - ry * d2x) / den, u = (rx * d1y - ry * d1x) / den;
+            if (t >= 0 && t <= 1 && u >= 0 && u <= 1) return rect_penetration(ego, obs, g);
+        }
+    double nx = (a[0] - b[0]) / best, ny = (a[1] - b[1]) / best;
+    g[0] = nx; g[1] = ny;
+    g[2] = nx * (-se * al[0] - ce * al[1]) + ny * (ce * al[0] - se * al[1]);
+    return best;
+}
+
+/* value of the collision row of node k in the units the reference writes it in */
+static double collision_row_ref(const igt_oracle_params *P, const prob_t *pr, int k, const double *z)
+{
+    if (pr->obs_psi) {
+        double ego[3] = { z[IX], z[IY], z[IPSI] }, ob[3] = { pr->obs[2 * k], pr->obs[2 * k + 1], pr->obs_psi[k] }, g[3];
+        return P->d_min + OBCA_MARGIN - rect_signed_distance(ego, ob, g);          /* mpc.py:216 */
+    }
+    double dx = z[IX] - pr->obs[2 * k], dy = z[IY] - pr->obs[2 * k + 1];
+    return P->d_min * P->d_min - dx * dx - dy * dy;                                 /* mpc.py:226 */
+}
+
+static void collision_row(const igt_oracle_params *P, const prob_t *pr, int k, const double *z, row_t *r)
+{
+    const double *o = pr->obs + 2 * k;
+    if (pr->obs_psi) {   /* mpc.py:211-221 with the duals maximised out: margin - signed rectangle distance, Gauss-Newton */
+        double ego[3] = { z[IX], z[IY], z[IPSI] }, ob[3] = { o[0], o[1], pr->obs_psi[k] }, g[3];
+        double sd = rect_signed_distance(ego, ob, g);
+        set_row(r, P->d_min + OBCA_MARGIN - sd, IX, -g[0], IY, -g[1]);
+        r->i2 = IPSI; r->g2 = -g[2];
+        return;
+    }
+    /* mpc.py:226 in the equivalent distance form d_min - |p - o| <= 0 */
     double dx = z[IX] - o[0], dy = z[IY] - o[1];
     double dist = hypot(dx, dy);
     if (dist < 1e-9) dist = 1e-9;
@@ -283,7 +396,7 @@ static int rows_eval(const igt_oracle_params *P, const prob_t *pr, int k, const 
     if (k == N) {
         set_row(&r[n++], z[IEY] - P->ey_lim, IEY, 1.0, -1, 0);
         set_row(&r[n++], -P->ey_lim - z[IEY], IEY, -1.0, -1, 0);
-        collision_row(P, z, pr->obs + 2 * N, &r[n++]);
+        collision_row(P, pr, N, z, &r[n++]);
         return n;
     }
     if (k >= 1) {
@@ -291,7 +404,7 @@ static int rows_eval(const igt_oracle_params *P, const prob_t *pr, int k, const 
         set_row(&r[n++], P->v_min - z[IV], IV, -1.0, -1, 0);      /* mpc.py:316 */
         set_row(&r[n++], z[IEY] - P->ey_lim, IEY, 1.0, -1, 0);    /* mpc.py:298 */
         set_row(&r[n++], -P->ey_lim - z[IEY], IEY, -1.0, -1, 0);  /* mpc.py:299 */
-        collision_row(P, z, pr->obs + 2 * k, &r[n++]);            /* mpc.py:226 */
+        collision_row(P, pr, k, z, &r[n++]);                      /* mpc.py:226 / :211-221 */
     }
     set_row(&r[n++], u[0] - P->a_max, IUA, 1.0, -1, 0);           /* mpc.py:319 */
     set_row(&r[n++], P->a_min - u[0], IUA, -1.0, -1, 0);          /* mpc.py:318 */
@@ -337,10 +450,7 @@ static double max_violation(const igt_oracle_params *P, const prob_t *pr, const 
     for (int k = 0; k <= N; k++) UPD(fabs(Z[k * NZ + IEY]) - P->ey_lim);
     for (int m_ = 0; m_ < P->n_cinf; m_++)
         UPD(P->cinf_A[m_][0] * Z[(N - 1) * NZ + IV] + P->cinf_A[m_][1] * U[2 * (N - 1)] - P->cinf_b[m_]);
-    for (int k = 1; k <= N; k++) {
-        double dx = Z[k * NZ + IX] - pr->obs[2 * k], dy = Z[k * NZ + IY] - pr->obs[2 * k + 1];
-        UPD(P->d_min * P->d_min - dx * dx - dy * dy);
-    }
+    for (int k = 1; k <= N; k++) UPD(collision_row_ref(P, pr, k, Z + k * NZ));
 #undef UPD
     return m;
 }
@@ -384,8 +494,11 @@ static double guess_merit(const igt_oracle_params *P, const prob_t *pr, const do
     }
     for (int k = 1; k <= N; k++) {
         viol += fmax(0.0, fabs(Z[k * NZ + IEY]) - P->ey_lim);
-        double dx = Z[k * NZ + IX] - pr->obs[2 * k], dy = Z[k * NZ + IY] - pr->obs[2 * k + 1];
-        viol += fmax(0.0, P->d_min - sqrt(dx * dx + dy * dy));
+        if (pr->obs_psi) viol += fmax(0.0, collision_row_ref(P, pr, k, Z + k * NZ));
+        else {
+            double dx = Z[k * NZ + IX] - pr->obs[2 * k], dy = Z[k * NZ + IY] - pr->obs[2 * k + 1];
+            viol += fmax(0.0, P->d_min - sqrt(dx * dx + dy * dy));
+        }
     }
     for (int m = 0; m < P->n_cinf; m++)
         viol += fmax(0.0, P->cinf_A[m][0] * Z[(N - 1) * NZ + IV] + P->cinf_A[m][1] * U[2 * (N - 1)] - P->cinf_b[m]);
@@ -477,7 +590,7 @@ static void add_dyn_hessian(const igt_oracle_params *P, const double *z, const d
 }
 
 /* status: 0 converged, 1 iteration limit, 2 x0 infeasible, 3 regularisation limit, 4 line search,
- * 5 stalled at an infeasible point */
+ * 5 stalled at an infeasible point, 6 stopped making progress at a point within the reference's tolerances */
 static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                      double *Zout, double *Uout, double *cost_out, double *viol_out, int *iters_out)
 {
@@ -485,7 +598,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
     int status = 1;
     *iters_out = 0;
     {   /* rows on x0 alone: mpc.py:316-317 and :298-299 at k = 0 */
-        double v = pr->x0[IV], ey = pr->x0[IEY], tol = 1e-9;
+        double v = pr->x0[IV], ey = pr->x0[IEY], tol = 1e-6;   /* igt_params.x0_tol */
         if (!(v >= P->v_min - tol && v <= P->v_max + tol && fabs(ey) <= P->ey_lim + tol)) {
             for (int i = 0; i < (N + 1) * NZ; i++) Zout[i] = NAN;
             for (int i = 0; i < N * 2; i++) Uout[i] = NAN;
@@ -564,6 +677,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                     double s = S[o + i], y = Y[o + i];
                     gw[r->i0] += r->g0 * s;
                     if (r->i1 >= 0) gw[r->i1] += r->g1 * s;
+                    if (r->i2 >= 0) gw[r->i2] += r->g2 * s;
                     double a = fabs(r->c + y);
                     if (a > rp) rp = a;
                     if (s > s_max) s_max = s;
@@ -594,7 +708,8 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
             need_jac = 0;
         }
         if (stat <= P->tol * fmax(1.0, s_max) && rp <= P->tol_rp && sy_max <= P->tol_comp) { status = 0; break; }
-        if (it == P->max_iter) break;
+        const int acceptable = P->acc_tol > 0 && stat <= P->acc_tol * fmax(1.0, s_max) && rp <= P->acc_rp && sy_max <= P->acc_comp;
+        if (it == P->max_iter) { if (acceptable) status = 6; break; }
         if (it >= P->stall_iter && rp > P->stall_rp) { status = 5; break; }
         /* barrier update */
         while (mu > P->mu_floor &&
@@ -629,6 +744,12 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                         Vxx[r->i1][r->i1] += sig * r->g1 * r->g1;
                         Vxx[r->i0][r->i1] += sig * r->g0 * r->g1;
                         Vxx[r->i1][r->i0] += sig * r->g0 * r->g1;
+                    }
+                    if (r->i2 >= 0) {
+                        Vx[r->i2] += r->g2 * gr;
+                        Vxx[r->i2][r->i2] += sig * r->g2 * r->g2;
+                        Vxx[r->i0][r->i2] += sig * r->g0 * r->g2; Vxx[r->i2][r->i0] += sig * r->g0 * r->g2;
+                        Vxx[r->i1][r->i2] += sig * r->g1 * r->g2; Vxx[r->i2][r->i1] += sig * r->g1 * r->g2;
                     }
                     if (r->has_h) {
                         Vxx[IX][IX] += s * r->hxx; Vxx[IX][IY] += s * r->hxy;
@@ -685,6 +806,12 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                         H[r->i0][r->i1] += sig * r->g0 * r->g1;
                         H[r->i1][r->i0] += sig * r->g0 * r->g1;
                     }
+                    if (r->i2 >= 0) {
+                        g[r->i2] += r->g2 * gr;
+                        H[r->i2][r->i2] += sig * r->g2 * r->g2;
+                        H[r->i0][r->i2] += sig * r->g0 * r->g2; H[r->i2][r->i0] += sig * r->g0 * r->g2;
+                        H[r->i1][r->i2] += sig * r->g1 * r->g2; H[r->i2][r->i1] += sig * r->g1 * r->g2;
+                    }
                     if (r->has_h) {
                         H[IX][IX] += s * r->hxx; H[IX][IY] += s * r->hxy;
                         H[IY][IX] += s * r->hxy; H[IY][IY] += s * r->hyy;
@@ -734,7 +861,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
             reg = fmax(fmax(reg * P->reg_up, P->reg_min), reg_hint);
             if (reg > P->reg_max) break;
         }
-        if (reg > P->reg_max) { status = 3; break; }
+        if (reg > P->reg_max) { status = acceptable ? 6 : 3; break; }
         /* forward passes */
         double tau = fmax(P->tau_min, 1.0 - mu);
         int accepted = 0;
@@ -758,7 +885,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                 for (int i = 0; i < n; i++) {
                     const row_t *r = &w->rows[o + i];
                     double y = Y[o + i];
-                    double dc = r->g0 * dw[r->i0] + (r->i1 >= 0 ? r->g1 * dw[r->i1] : 0.0);
+                    double dc = r->g0 * dw[r->i0] + (r->i1 >= 0 ? r->g1 * dw[r->i1] : 0.0) + (r->i2 >= 0 ? r->g2 * dw[r->i2] : 0.0);
                     double dy = -(r->c + y) - dc;
                     if (dy < 0 && -dy * alpha > tau * y) alpha = tau * y / (-dy);
                 }
@@ -796,7 +923,7 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
                 for (int i = 0; i < n; i++) {
                     const row_t *r = &w->rows[o + i];
                     double s = S[o + i], y = Y[o + i];
-                    double dc = r->g0 * dw[r->i0] + (r->i1 >= 0 ? r->g1 * dw[r->i1] : 0.0);
+                    double dc = r->g0 * dw[r->i0] + (r->i1 >= 0 ? r->g1 * dw[r->i1] : 0.0) + (r->i2 >= 0 ? r->g2 * dw[r->i2] : 0.0);
                     double yn = y - alpha * (r->c + y) - dc;
                     double sn = s + (alpha * (s * r->c + mu) + s * dc) / y;
                     if (yn < (1 - tau) * y) { fail = 1; break; }        /* fraction to the boundary */
@@ -840,9 +967,9 @@ static int solve_one(const igt_oracle_params *P, const prob_t *pr, work_t *w,
         } else {
             reg = fmax(reg * P->reg_up, P->reg_min);
             ls_fail++;
-            if (reg > P->reg_max || ls_fail >= P->max_ls_fail) { status = 4; break; }
+            if (reg > P->reg_max || ls_fail >= P->max_ls_fail) { status = acceptable ? 6 : 4; break; }
         }
-        if (trials >= P->max_trials) { status = 1; break; }
+        if (trials >= P->max_trials) { status = (!accepted && acceptable) ? 6 : 1; break; }
     }
     memcpy(Zout, Z, sizeof(double) * NZ * (N + 1));
     memcpy(Uout, U, sizeof(double) * 2 * N);
@@ -862,6 +989,7 @@ void igt_oracle_default_options(igt_oracle_params *P)
     P->max_ls_fail = 1000; P->max_trials = 1000000; P->predict_alpha = 1; P->alpha_safety = 0.99;
     P->reg_jump = 1.1;
     P->stall_iter = 16; P->stall_rp = 1e-2;
+    P->acc_tol = 1e-3; P->acc_rp = 1e-6; P->acc_comp = 1e-4;
 }
 
 size_t igt_oracle_params_size(void) { return sizeof(igt_oracle_params); }
@@ -931,6 +1059,7 @@ typedef struct {
     double *Z, *U, *cost, *viol;
     int *status, *iters;
     int next;                /* shared work counter (chunks of 4 problems) */
+    const double *obs_psi;   /* [B][N+1] or NULL */
 } batch_t;
 
 static void *batch_worker(void *arg)
@@ -946,7 +1075,8 @@ static void *batch_worker(void *arg)
         for (int b = lo; b < hi; b++) {
             prob_t pr = { bt->x0 + 7 * (size_t)b, bt->u_prev + 2 * (size_t)b, bt->curv + 3 * (size_t)b,
                           bt->obs + (size_t)b * (N + 1) * 2, bt->ctx ? bt->ctx + 4 * (size_t)b : NULL,
-                          bt->u_init ? bt->u_init + (size_t)b * N * 2 : NULL };
+                          bt->u_init ? bt->u_init + (size_t)b * N * 2 : NULL,
+                          bt->obs_psi ? bt->obs_psi + (size_t)b * (N + 1) : NULL };
             bt->status[b] = solve_one(P, &pr, w, bt->Z + (size_t)b * (N + 1) * NZ, bt->U + (size_t)b * N * 2,
                                       bt->cost + b, bt->viol + b, bt->iters + b);
         }
@@ -955,13 +1085,13 @@ static void *batch_worker(void *arg)
     return NULL;
 }
 
-/* n_threads <= 0: use every online core */
-int igt_oracle_solve_batch(const igt_oracle_params *P, int nb, const double *x0, const double *u_prev,
-                           const double *curv, const double *obs, const double *ctx,
-                           const double *u_init, double *Z, double *U, double *cost, double *viol,
-                           int *status, int *iters, int n_threads)
+/* n_threads <= 0: use every online core.  obs_psi[B][N+1] != NULL selects the OBCA collision rows. */
+int igt_oracle_solve_batch_obca(const igt_oracle_params *P, int nb, const double *x0, const double *u_prev,
+                                const double *curv, const double *obs, const double *obs_psi, const double *ctx,
+                                const double *u_init, double *Z, double *U, double *cost, double *viol,
+                                int *status, int *iters, int n_threads)
 {
-    batch_t bt = { P, nb, x0, u_prev, curv, obs, ctx, u_init, Z, U, cost, viol, status, iters, 0 };
+    batch_t bt = { P, nb, x0, u_prev, curv, obs, ctx, u_init, Z, U, cost, viol, status, iters, 0, obs_psi };
     if (n_threads <= 0) n_threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
     if (n_threads > 256) n_threads = 256;
     if (n_threads > (nb + 3) / 4) n_threads = (nb + 3) / 4;
@@ -969,5 +1099,33 @@ int igt_oracle_solve_batch(const igt_oracle_params *P, int nb, const double *x0,
     pthread_t th[256];
     for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, batch_worker, &bt);
     for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    return 0;
+}
+
+int igt_oracle_solve_batch(const igt_oracle_params *P, int nb, const double *x0, const double *u_prev,
+                           const double *curv, const double *obs, const double *ctx,
+                           const double *u_init, double *Z, double *U, double *cost, double *viol,
+                           int *status, int *iters, int n_threads)
+{
+    return igt_oracle_solve_batch_obca(P, nb, x0, u_prev, curv, obs, NULL, ctx, u_init, Z, U, cost, viol, status, iters, n_threads);
+}
+
+/* OBCA mode: max row value (reference units) of given trajectories */
+int igt_oracle_viol_obca(const igt_oracle_params *P, int nb, const double *x0, const double *u_prev, const double *curv,
+                         const double *obs, const double *obs_psi, const double *Z, const double *U, double *viol)
+{
+    int N = P->N;
+    for (int b = 0; b < nb; b++) {
+        prob_t pr = { x0 + 7 * (size_t)b, u_prev + 2 * (size_t)b, curv + 3 * (size_t)b, obs + (size_t)b * (N + 1) * 2, NULL, NULL,
+                      obs_psi + (size_t)b * (N + 1) };
+        viol[b] = max_violation(P, &pr, Z + (size_t)b * (N + 1) * NZ, U + (size_t)b * N * 2);
+    }
+    return 0;
+}
+
+/* signed rectangle distance and gradient for n pose pairs (tests) */
+int igt_oracle_rect_sdist(int n, const double *ego, const double *obs, double *d, double *g)
+{
+    for (int i = 0; i < n; i++) d[i] = rect_signed_distance(ego + 3 * i, obs + 3 * i, g + 3 * i);
     return 0;
 }

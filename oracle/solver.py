@@ -51,6 +51,11 @@ class Options:
     stall_iter = 16
     stall_rp = 1e-2
     alpha_safety = 0.99
+    # reference-tolerance exit (status 6): no further progress at a point within the reference's IPOPT tolerances
+    # (mpc.py:133-135 tol = dual_inf_tol = constr_viol_tol = 1e-3, IPOPT default compl_inf_tol 1e-4; primal bound 1e-6)
+    acc_tol = 1e-3
+    acc_rp = 1e-6
+    acc_comp = 1e-4
 
 
 # --------------------------------------------------------------------------------------
@@ -153,7 +158,7 @@ def all_rows_values(P, prob, Z, U):
     return out
 
 
-def x0_feasible(P, prob, tol=1e-9):
+def x0_feasible(P, prob, tol=1e-6):
     """Rows that involve only the fixed initial state (mpc.py:316-317 at k=0, :298-299 at
     k=0).  If x0 violates them the reference NLP is infeasible."""
     v, ey = prob.x0[D.IV], prob.x0[D.IEY]
@@ -224,7 +229,7 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
           verbose=False):
     """Returns a Result with status (0 converged, 1 iteration limit, 2 x0 violates its own
     rows, 3 regularisation limit in the backward pass, 4 line search failed, 5 stalled at an
-    infeasible point), iters, Z[N+1,7],
+    infeasible point, 6 no further progress at a point within the reference's IPOPT tolerances), iters, Z[N+1,7],
     U[N,2], cost, viol (max inequality-row violation in the reference's units)."""
     opt = opt or Options()
     N = P.N
@@ -303,7 +308,10 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
         if stat <= opt.tol * max(1.0, s_max) and rp <= opt.tol_rp and sy_max <= opt.tol_comp:
             res.status = 0
             break
+        acceptable = opt.acc_tol > 0 and stat <= opt.acc_tol * max(1.0, s_max) and rp <= opt.acc_rp and sy_max <= opt.acc_comp
         if it == opt.max_iter:
+            if acceptable:
+                res.status = 6
             break
         if it >= opt.stall_iter and rp > opt.stall_rp:      # stalled at an infeasible point
             res.status = 5
@@ -377,7 +385,7 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
             if reg > opt.reg_max:
                 break
         if reg > opt.reg_max:
-            res.status = 3
+            res.status = 6 if acceptable else 3
             break
         # ---- sweeps 4..: closed-loop forward pass with fraction-to-boundary -------------
         tau = max(opt.tau_min, 1.0 - mu)
@@ -427,10 +435,14 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
             if not fail:
                 Cn = all_rows_values(P, prob, Zn, Un)
                 phin, thetan = barrier_cost(Zn, Un, Yn, mu), infeas(Cn, Yn)
+                if verbose > 1:
+                    print(f"      trial alpha {alpha:.3e}: dphi {phin - phi:+.3e} (need < {-opt.eps_phi * abs(phi):.1e}) theta {theta:.3e} -> {thetan:.3e}")
                 if np.isfinite(phin) and (phin < phi - opt.eps_phi * abs(phi) or thetan < theta * (1 - opt.gamma_theta)
                                           or (thetan <= opt.theta_small and phin <= phi + opt.eps_phi * max(1, abs(phi)))):
                     accepted = True
                     break
+            elif verbose > 1:
+                print(f"      trial alpha {alpha:.3e}: fraction-to-boundary / non-finite")
             alpha *= 0.5
         if accepted:
             Z, U, Y, S, C = Zn, Un, Yn, Sn, Cn
@@ -439,7 +451,7 @@ def solve(P: nlp.Params, prob: nlp.Problem, mlp: nlp.MLPTerm = None, opt: Option
         else:
             reg = max(reg * opt.reg_up, opt.reg_min)
             if reg > opt.reg_max:
-                res.status = 4
+                res.status = 6 if acceptable else 4
                 break
     res.Z, res.U = Z, U
     res.cost = nlp.cost(P, prob, Z, U, mlp)

@@ -15,7 +15,7 @@ _dp = C.POINTER(C.c_double)
 def build():
     src = os.path.join(_HERE, "hostsim.cu")
     deps = [src] + [os.path.join(_HERE, "..", "..", "igt_mpc_int_b200", "csrc", f)
-                    for f in ("solver_core.cuh", "params_host.hpp")]
+                    for f in ("solver_core.cuh", "params_host.hpp", "obca.cuh")]
     if not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
                                "-Xcompiler", "-fPIC", "-shared", "-o", _SO, src])
@@ -78,3 +78,24 @@ def rollout(p, prec, z0, U, curv, jac=False):
     rc = lib().hostsim_rollout(C.byref(p), B, prec, _ptr(z0), _ptr(U), _ptr(curv), _ptr(Z), _ptr(A), _ptr(Bm))
     assert rc == 0, "value-only and sensitivity RK4 steps disagree"
     return (Z, A, Bm) if jac else Z
+
+
+def solve_obca(p, x0, u_prev, curv, obs, obs_psi, u_init=None):
+    """product solver code (OBCA collision rows, fp64) on the CPU"""
+    x0, u_prev, curv, obs, obs_psi, u_init = map(_c, (x0, u_prev, curv, obs, obs_psi, u_init))
+    B, N = x0.shape[0], p.N
+    Z = np.empty((B, N + 1, 7)); U = np.empty((B, N, 2)); cost = np.empty(B); viol = np.empty(B)
+    status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+    rc = lib().hostsim_solve_obca(C.byref(p), B, _ptr(x0), _ptr(u_prev), _ptr(curv), _ptr(obs), _ptr(obs_psi), _ptr(u_init),
+                                  _ptr(Z), _ptr(U), _ptr(cost), _ptr(viol), status.ctypes.data_as(C.POINTER(C.c_int)),
+                                  iters.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return dict(Z=Z, U=U, cost=cost, viol=viol, status=status, iters=iters)
+
+
+def rect_sdist(ego, obs):
+    ego, obs = _c(ego), _c(obs)
+    n = ego.shape[0]
+    d = np.empty(n); g = np.empty((n, 3))
+    lib().hostsim_rect_sdist(n, _ptr(ego), _ptr(obs), _ptr(d), _ptr(g))
+    return d, g

@@ -8,9 +8,9 @@
 
 using namespace igt;
 
-template <typename T>
+template <typename T, bool OBCA = false>
 static int run(const igt_params *p, int B, const double *x0, const double *u_prev, const double *curv,
-               const double *obs, const double *ctx, const double *u_init, double *x, double *u, double *cost,
+               const double *obs, const double *obs_psi, const double *ctx, const double *u_init, double *x, double *u, double *cost,
                double *viol, int *status, int *iters, int n_layers, const int *dims, const double *const *W,
                const double *const *b, const double *Wn, const double *mu_f, double sigma_t, double mu_t)
 {
@@ -31,12 +31,13 @@ static int run(const igt_params *p, int B, const double *x0, const double *u_pre
         for (int i = 0; i < 6; i++) P.mu_f[i] = T(mu_f[i]);
         P.sigma_t = T(sigma_t); P.mu_t = T(mu_t);
     }
-    WsLayout L; L.init(p->N, p->n_cinf);
+    WsLayout L; L.init(p->N, p->n_cinf, OBCA ? NGE_OBCA : NGE, OBCA ? NHE_OBCA : NHE);
     std::vector<T> ws((size_t)L.total * 32);
     std::vector<T> scratch((size_t)12 * width);
     std::vector<double> guess((size_t)2 * p->N);
     ProbIO io = { x0, u_prev, curv, obs, ctx, u_init, x, u, cost, viol, status, iters };
-    for (long q = 0; q < B; q++) solve_problem<T>(P, io, ws.data(), q % 32, q, guess.data(), scratch.data(), width);
+    io.obs_psi = obs_psi;
+    for (long q = 0; q < B; q++) solve_problem<T, OBCA>(P, io, ws.data(), q % 32, q, guess.data(), scratch.data(), width);
     return 0;
 }
 
@@ -49,8 +50,25 @@ int hostsim_solve(const igt_params *p, int B, const double *x0, const double *u_
                   const double *const *b, const double *Wn, const double *mu_f, double sigma_t, double mu_t)
 {
     if (p->precision == IGT_PREC_F64)
-        return run<double>(p, B, x0, u_prev, curv, obs, ctx, u_init, x, u, cost, viol, status, iters, n_layers, dims, W, b, Wn, mu_f, sigma_t, mu_t);
-    return run<float>(p, B, x0, u_prev, curv, obs, ctx, u_init, x, u, cost, viol, status, iters, n_layers, dims, W, b, Wn, mu_f, sigma_t, mu_t);
+        return run<double>(p, B, x0, u_prev, curv, obs, nullptr, ctx, u_init, x, u, cost, viol, status, iters, n_layers, dims, W, b, Wn, mu_f, sigma_t, mu_t);
+    return run<float>(p, B, x0, u_prev, curv, obs, nullptr, ctx, u_init, x, u, cost, viol, status, iters, n_layers, dims, W, b, Wn, mu_f, sigma_t, mu_t);
+}
+
+// OBCA collision mode (obs_psi[B][N+1] obstacle headings), fp64, 'mpc' cost
+int hostsim_solve_obca(const igt_params *p, int B, const double *x0, const double *u_prev, const double *curv,
+                       const double *obs, const double *obs_psi, const double *u_init, double *x, double *u, double *cost,
+                       double *viol, int *status, int *iters)
+{
+    return run<double, true>(p, B, x0, u_prev, curv, obs, obs_psi, nullptr, u_init, x, u, cost, viol, status, iters, 0,
+                             nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0);
+}
+
+// rectangle signed distance + gradient (csrc/obca.cuh) for n pose pairs: ego[n][3], obs[n][3] -> d[n], g[n][3]
+int hostsim_rect_sdist(int n, const double *ego, const double *obs, double *d, double *g)
+{
+    for (int i = 0; i < n; i++)
+        d[i] = obca_rect_sdist(ego[3 * i], ego[3 * i + 1], ego[3 * i + 2], obs[3 * i], obs[3 * i + 1], obs[3 * i + 2], g + 3 * i);
+    return 0;
 }
 
 // rollout of the product's templated dynamics on the host (fp32 plain / fp64), with sensitivities

@@ -305,3 +305,157 @@ def test_latency_path_is_bit_identical_to_throughput_kernel():
                 for k in ("status", "iters", "cost", "viol", "u", "x"):
                     assert np.array_equal(out[0][i][k], out[1][i][k], equal_nan=True), (N, prec, B, i, k)
         s.close()
+
+
+def test_concurrent_handles_and_streams_match_sequential():
+    """The boundary is re-entrant (include/igt_mpc.h "Concurrency"): two handles with different horizons running at
+    the same time on two streams, and two calls on ONE handle issued on two streams, give the results of the same
+    calls made one after the other."""
+    import torch
+    from igt_mpc_int_b200 import scenarios as S
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    cases = {}
+    for N, B, seed in ((40, 2048, 5), (20, 2048, 6), (10, 1024, 7)):
+        pb = S.mid_episode(B, N=N, seed=seed)
+        cases[N] = dict(s=_solver(N), args=tuple(t(a) for a in (pb.x0, pb.u_prev, pb.curv, pb.obs)))
+    # sequential reference on the default stream
+    ref = {}
+    for N, c in cases.items():
+        o = c["s"].solve_batch_device(*c["args"])
+        torch.cuda.synchronize()
+        ref[N] = {k: v.clone() for k, v in o.items()}
+    # all three handles at once, each on its own stream, several times over (params of different N live in different slots)
+    streams = {N: torch.cuda.Stream() for N in cases}
+    outs = {N: [] for N in cases}
+    for rep in range(3):
+        for N, c in cases.items():
+            with torch.cuda.stream(streams[N]):
+                outs[N].append(c["s"].solve_batch_device(*c["args"]))
+    torch.cuda.synchronize()
+    for N in cases:
+        for o in outs[N]:
+            for k in ("status", "iters"):
+                assert torch.equal(o[k], ref[N][k]), (N, k)
+            ok = ref[N]["status"] == 0
+            assert torch.equal(o["u"][ok], ref[N]["u"][ok]) and torch.equal(o["cost"][ok], ref[N]["cost"][ok])
+    # one handle, two streams, different inputs: the second call must not start on the shared workspace early
+    c = cases[40]
+    pb2 = S.mid_episode(2048, N=40, seed=99)
+    args2 = tuple(t(a) for a in (pb2.x0, pb2.u_prev, pb2.curv, pb2.obs))
+    ref2 = {k: v.clone() for k, v in c["s"].solve_batch_device(*args2).items()}
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(s1):
+        o1 = c["s"].solve_batch_device(*c["args"])
+    with torch.cuda.stream(s2):
+        o2 = c["s"].solve_batch_device(*args2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1["status"], ref[40]["status"]) and torch.equal(o2["status"], ref2["status"])
+    ok1, ok2 = ref[40]["status"] == 0, ref2["status"] == 0
+    assert torch.equal(o1["u"][ok1], ref[40]["u"][ok1]) and torch.equal(o2["u"][ok2], ref2["u"][ok2])
+    # more handles than constant-memory slots (8): the ninth shares a slot, still correct
+    extra = [_solver(10, max_iter=30 + i) for i in range(9)]
+    pb3 = S.mid_episode(256, N=10, seed=3)
+    a3 = tuple(t(a) for a in (pb3.x0, pb3.u_prev, pb3.curv, pb3.obs))
+    r_first = {k: v.clone() for k, v in extra[0].solve_batch_device(*a3).items()}
+    for e in extra[1:]:
+        e.solve_batch_device(*a3)
+    r_again = extra[0].solve_batch_device(*a3)
+    torch.cuda.synchronize()
+    assert torch.equal(r_first["status"], r_again["status"]) and torch.equal(r_first["iters"], r_again["iters"])
+    for e in extra:
+        e.close()
+    for c in cases.values():
+        c["s"].close()
+
+
+def test_acceptable_status_matches_oracle(oracle_params):
+    """IGT_STATUS_ACCEPTABLE (6): solves that end in a failure at a point within the reference's own tolerances are
+    the same on the GPU and in the oracle, meet the north star's violation bound, and never replace a tight
+    convergence (with the exit disabled exactly the same problems converge)."""
+    from oracle import c_oracle
+    from igt_mpc_int_b200 import scenarios as S
+    pb = S.mid_episode(4096, N=40, seed=2026)
+    s = _solver(40)
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    s.close()
+    o = c_oracle.COracle(oracle_params[40], max_iter=60).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    assert (o["status"] == 6).sum() >= 3
+    assert np.mean(r["status"] == o["status"]) > 0.995
+    acc = (r["status"] == 6) & (o["status"] == 6)
+    assert acc.sum() >= 0.6 * (o["status"] == 6).sum()
+    assert np.max(r["viol"][r["status"] == 6]) <= 1e-6
+    s = _solver(40, acc_tol=0.0)
+    r0 = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    s.close()
+    assert (r0["status"] == 6).sum() == 0 and np.array_equal(r0["status"] == 0, r["status"] == 0)
+    assert np.all(np.isin(r0["status"][r["status"] == 6], (1, 3, 4)))
+
+
+def test_obca_mode_matches_oracle(oracle_params):
+    """collision_avoidance_type 'obca' (mpc.py:42-43, :170-175, :211-221) on the GPU: the dual-eliminated row
+    (csrc/obca.cuh) through igt_solve_host with obs_psi, against the oracle's C port on 1024 problems, plus a
+    parallel-faces case (the kink of the rectangle distance in psi)."""
+    from oracle import nlp, c_oracle, obca
+    from igt_mpc_int_b200 import scenarios as S
+    N, B = 40, 1024
+    P = nlp.Params(N=N, d_min=0.0, cinf_A=oracle_params[40].cinf_A, cinf_b=oracle_params[40].cinf_b)
+    pb = S.mid_episode(B, N=N, seed=5)
+    s = _solver(N, d_min=0.0)
+    r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, obs_psi=pb.obs_psi)
+    o = c_oracle.COracle(P, max_iter=s.params.max_iter).solve(pb.x0, pb.u_prev, pb.curv, pb.obs, obs_psi=pb.obs_psi)
+    assert np.mean(r["status"] == o["status"]) > 0.99
+    ok = (o["status"] == 0) & (r["status"] == 0)
+    assert ok.sum() > 0.85 * B
+    assert np.max(relerr(r["cost"][ok], o["cost"][ok])) < 1e-4
+    assert np.max(np.abs(r["u"][ok] - o["U"][ok])) < 1e-3
+    assert np.max(r["viol"][ok]) <= 1e-6
+    # the reported violation is the reference's OBCA row, and the rows do bind
+    v = c_oracle.COracle(P).viol_obca(pb.x0[ok], pb.u_prev[ok], pb.curv[ok], pb.obs[ok], pb.obs_psi[ok], r["x"][ok], r["u"][ok])
+    assert np.max(np.abs(np.maximum(v, 0) - r["viol"][ok])) < 1e-9
+    ev = s.evaluate(pb.x0[ok], pb.u_prev[ok], pb.curv[ok], pb.obs[ok], r["u"][ok], obs_psi=pb.obs_psi[ok])
+    assert np.max(np.abs(ev["viol"] - np.maximum(v, 0))) < 1e-9
+    idx = np.where(ok)[0]
+    dmin = np.array([min(obca.rect_distance(r["x"][i][k, [0, 1, 6]], np.array([pb.obs[i, k, 0], pb.obs[i, k, 1], pb.obs_psi[i, k]]))[0]
+                         for k in range(1, N + 1)) for i in idx[:256]])
+    assert (dmin < 1e-5).sum() >= 3 and dmin.min() > -1e-6
+    # the circle rows (d_min = 5.6) on the same problems give different plans: the mode switch is real
+    s2 = _solver(N)
+    rc = s2.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs)
+    both = ok & (rc["status"] == 0)
+    assert np.max(np.abs(rc["u"][both] - r["u"][both])) > 1e-2
+    s2.close()
+    # parallel faces: a car standing in the ego's lane, same heading -- nose-to-tail distance with a kink in psi
+    x0 = np.array([[5.0, 2.8, 5.0, 0.0, 0.0, 3.0, 0.0]]); up = np.zeros((1, 2)); cv = np.array([[1e30, 1e30, 0.0]])
+    ob = np.tile(np.array([14.0, 2.8]), (1, N + 1, 1)); op = np.zeros((1, N + 1))
+    rk = s.solve_batch(x0, up, cv, ob, obs_psi=op)
+    okk = c_oracle.COracle(P, max_iter=s.params.max_iter).solve(x0, up, cv, ob, obs_psi=op)
+    assert rk["status"][0] == okk["status"][0]
+    if rk["status"][0] == 0:
+        assert abs(rk["cost"][0] - okk["cost"][0]) < 1e-4 * max(1.0, abs(okk["cost"][0]))
+        assert rk["x"][0][-1, 0] <= 14.0 - 4.47 + 1e-6         # stops behind the obstacle's tail
+    s.close()
+
+
+def test_planner_obca_mode_protocol():
+    """MPC_Planner(ca_type='obca') (mpc.py:40-43): same protocol, obstacle heading taken from the forecasts."""
+    from types import SimpleNamespace as NS
+    from igt_mpc_int_b200.planner import MPC_Planner
+    from igt_mpc_int_b200 import reference_track as RT
+    N = 20
+    routes = ['13', '23']
+    ref = [dict(K=np.zeros(151)), dict(K=np.zeros(151))]
+    agents = [dict(type='mpc', state=NS(x=5.0, y=2.8, s=5.0, ey=0.0, epsi=0.0, v=3.0, heading=0.0)),
+              dict(type='mpc', state=NS(x=0.0, y=-20.0, s=0.0, ey=0.0, epsi=0.0, v=0.0, heading=0.0))]
+    pl = MPC_Planner(N=N, dt=0.1, agents=agents, goals=None, ca_radius=2.8, ref=ref, road_dim=(11.4, 50), routes=routes,
+                     ds_right=8.6, index=0, num_rk4_steps=4, ca_type='obca')
+    assert pl.d_min == 0
+    pl.update_initial_condition(agents[0], NS(a=0.0, df=0.0))
+    obst = [NS(x=13.0, y=3.4, s=0.0, ey=0.0, epsi=0.0, v=0.0, heading=0.9) for _ in range(N + 1)]
+    own = [agents[0]['state']] * (N + 1)
+    pl.update_predictions([own, obst])
+    x, u, ok = pl.solve()
+    assert ok and x.shape == (7, N + 1) and u.shape == (2, N)
+    from oracle import obca
+    d = min(obca.rect_distance(x[[0, 1, 6], k], np.array([13.0, 3.4, 0.9]))[0] for k in range(1, N + 1))
+    assert d >= 1e-6 - 1e-7

@@ -90,3 +90,27 @@ def test_core_iteration_and_trial_budgets_match_oracle(oracle_params, cinf):
     o = c_oracle.COracle(oracle_params[40], max_iter=p.max_iter, max_trials=p.max_trials).solve(pb.x0, pb.u_prev, pb.curv, pb.obs)
     assert np.mean(r["status"] == o["status"]) >= 0.99
     assert (r["status"] != 0).sum() > 0
+
+
+def test_product_solver_code_obca_mode_matches_oracle(oracle_params):
+    """The product's per-thread solver code with the OBCA collision rows (csrc/obca.cuh, Ws<T, 32, true>) run on the CPU
+    reproduces the oracle's C port: same statuses, iteration counts and optima (mpc.py:211-221, d_min = 0)."""
+    from oracle import nlp, c_oracle
+    N = 40
+    P = nlp.Params(N=N, d_min=0.0, cinf_A=oracle_params[40].cinf_A, cinf_b=oracle_params[40].cinf_b)
+    pb = S.mid_episode(64, N=N, seed=5)
+    p = H.default_params(1)
+    p.N = N; p.d_min = 0.0
+    p.set_cinf(P.cinf_A, P.cinf_b)
+    r = H.solve_obca(p, pb.x0, pb.u_prev, pb.curv, pb.obs, pb.obs_psi)
+    o = c_oracle.COracle(P, max_iter=p.max_iter).solve(pb.x0, pb.u_prev, pb.curv, pb.obs, obs_psi=pb.obs_psi)
+    assert np.array_equal(r["status"], o["status"]) and np.mean(r["iters"] == o["iters"]) > 0.95
+    ok = o["status"] == 0
+    assert ok.sum() >= 50
+    assert np.max(np.abs(r["cost"][ok] - o["cost"][ok]) / np.maximum(1.0, np.abs(o["cost"][ok]))) < 1e-9
+    assert np.max(np.abs(r["U"][ok] - o["U"][ok])) < 1e-6 and r["viol"][ok].max() <= 1e-9
+    # the rows bind: some solutions sit on the rectangle-distance margin
+    from oracle import obca
+    dmin = [min(obca.rect_distance(o["Z"][i][k, [0, 1, 6]], np.array([pb.obs[i, k, 0], pb.obs[i, k, 1], pb.obs_psi[i, k]]))[0]
+                for k in range(1, N + 1)) for i in np.where(ok)[0]]
+    assert min(dmin) < 1e-5 and min(dmin) > -1e-9

@@ -133,3 +133,36 @@ def test_obca_mpc_eliminated_rows_vs_reference_formulation_with_explicit_duals()
     U = unpack(res.x)[0]
     assert abs(res.fun - r.cost) < 1e-5 * max(1.0, abs(r.cost)), (res.fun, r.cost)
     assert np.max(np.abs(U - r.U)) < 2e-3
+
+
+def test_c_port_of_the_rectangle_distance_equals_the_python_statement():
+    """oracle/igt_oracle.c restates oracle/obca.rect_distance (incl. the penetration branch)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(11)
+    pairs = _poses(rng, 200, 2.5, 12.0) + _poses(rng, 100, 0.1, 2.5)
+    ego = np.array([p[0] for p in pairs]); obs = np.array([p[1] for p in pairs])
+    d, g = c_oracle.rect_sdist(ego, obs)
+    for i in range(len(pairs)):
+        do, go = obca.rect_distance(ego[i], obs[i])
+        assert abs(do - d[i]) < 1e-12 and np.max(np.abs(go - g[i])) < 1e-11
+    assert (d < 0).sum() > 20 and (d > 0).sum() > 150
+
+
+def test_c_oracle_obca_mode_equals_python_oracle():
+    """same algorithm, same rows: the C port reproduces the python oracle's OBCA solves"""
+    from oracle import nlp, solver, c_oracle
+    from igt_mpc_int_b200 import scenarios as S
+    N = 20
+    base = nlp.Params(N=40)
+    P = nlp.Params(N=N, d_min=0.0, cinf_A=base.cinf_A, cinf_b=base.cinf_b)        # mpc.py:42-43: d_min = 0 in OBCA mode
+    pb = S.mid_episode(16, N=N, seed=5)
+    assert np.abs(pb.obs_psi).max() > 0.5
+    o = c_oracle.COracle(P, max_iter=60).solve(pb.x0, pb.u_prev, pb.curv, pb.obs, obs_psi=pb.obs_psi)
+    opt = solver.Options(); opt.max_iter = 60
+    for i in (0, 2, 5):
+        prob = nlp.Problem(x0=pb.x0[i], u_prev=pb.u_prev[i], curv=tuple(pb.curv[i]), obs=pb.obs[i], obs_psi=pb.obs_psi[i])
+        r = solver.solve(P, prob, opt=opt)
+        assert r.status == o["status"][i] and r.iters == o["iters"][i]
+        if r.status == 0:
+            assert abs(r.cost - o["cost"][i]) < 1e-9 and np.max(np.abs(r.U - o["U"][i])) < 1e-7
+            assert abs(r.viol - o["viol"][i]) < 1e-12
