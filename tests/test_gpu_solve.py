@@ -445,7 +445,7 @@ def test_planner_obca_mode_protocol():
     N = 20
     routes = ['13', '23']
     ref = [dict(K=np.zeros(151)), dict(K=np.zeros(151))]
-    agents = [dict(type='mpc', state=NS(x=5.0, y=2.8, s=5.0, ey=0.0, epsi=0.0, v=3.0, heading=0.0)),
+    agents = [dict(type='mpc', state=NS(x=5.0, y=2.8, s=5.0, ey=0.0, epsi=0.0, v=1.0, heading=0.0)),
               dict(type='mpc', state=NS(x=0.0, y=-20.0, s=0.0, ey=0.0, epsi=0.0, v=0.0, heading=0.0))]
     pl = MPC_Planner(N=N, dt=0.1, agents=agents, goals=None, ca_radius=2.8, ref=ref, road_dim=(11.4, 50), routes=routes,
                      ds_right=8.6, index=0, num_rk4_steps=4, ca_type='obca')
