@@ -34,33 +34,48 @@ METRIC = "converged MPC solves/sec"
 UNIT = "solves/s"
 
 WORKLOADS = {
-    # name: (generator, problems per GPU, horizon, mode)
-    "cfg2_mpc_sc1-8_4096ic": ("mid_episode", 32768, 40, "mpc"),
-    "cfg2_episode_start": ("episode_start", 32768, 40, "mpc"),
-    "cfg4_frenet_65536": ("mid_episode", 65536, 40, "mpc"),
-    "cfg5_131072_N40": ("mid_episode", 131072, 40, "mpc"),
-    "cfg5_131072_N20": ("mid_episode", 131072, 20, "mpc"),
-    "cfg5_131072_N10": ("mid_episode", 131072, 10, "mpc"),
-    "cfg3_gt_mpc_16384": ("mid_episode", 16384, 40, "gt_mpc"),
+    # name: (generator, problems [per GPU if weak, in total if strong], horizon, mode, scaling, value-network hidden layers)
+    "cfg2_mpc_sc1-8_4096ic": ("mid_episode", 32768, 40, "mpc", "weak", None),
+    "cfg2_episode_start": ("episode_start", 32768, 40, "mpc", "weak", None),
+    # BASELINE config 4: 65536 sampled states in TOTAL, sharded over the GPUs (strong scaling)
+    "cfg4_frenet_65536": ("mid_episode", 65536, 40, "mpc", "strong", None),
+    # BASELINE config 5: 2^20 problems over 8 GPUs = 131072 per GPU, horizon sweep (weak: per-GPU share fixed)
+    "cfg5_131072_N40": ("mid_episode", 131072, 40, "mpc", "weak", None),
+    "cfg5_131072_N20": ("mid_episode", 131072, 20, "mpc", "weak", None),
+    "cfg5_131072_N10": ("mid_episode", 131072, 10, "mpc", "weak", None),
+    # BASELINE config 3: gt_mpc, random-init value network, both shapes the reference ships (sc*_config.yaml num_layers 2 / 3)
+    "cfg3_gt_mpc_16384": ("mid_episode", 16384, 40, "gt_mpc", "weak", (128, 128)),
+    "cfg3_gt_mpc_16384_3hidden": ("mid_episode", 16384, 40, "gt_mpc", "weak", (128, 128, 128)),
 }
 DEFAULT_WORKLOAD = "cfg2_mpc_sc1-8_4096ic"
 MAX_ITER_DEFAULT = 60        # the library's default iteration cap (igt_default_params); the CPU arm uses the same
 
 
-def make_problems(name, rank):
-    from igt_mpc_int_b200 import scenarios as S
-    gen, B, N, mode = WORKLOADS[name]
-    seed = {"cfg4_frenet_65536": 4}.get(name, 2026) + 1000 * rank      # seeds 2026+sc / 4
-    cache = os.path.join("/tmp", "igt_bench_%s_r%d.npz" % (name, rank))
+def make_problems(name, rank, world=1, scaling=None):
+    """This rank's problems.  weak: every rank draws its own batch (seed + 1000 rank); strong: every rank draws the
+    SAME full batch and keeps its contiguous block (sharding.shard_range)."""
+    from igt_mpc_int_b200 import scenarios as S, sharding
+    gen, B, N, mode, default_scaling, _ = WORKLOADS[name]
+    scaling = scaling or default_scaling
+    strong = scaling == "strong"
+    seed = {"cfg4_frenet_65536": 4}.get(name, 2026) + (0 if strong else 1000 * rank)      # SURVEY 8(d): seeds 2026+sc / 4
+    cache = os.path.join("/tmp", "igt_bench_%s_s%d.npz" % (name, seed))
     if os.path.exists(cache):
         d = np.load(cache)
-        return d["x0"], d["up"], d["cv"], d["ob"], d["ctx"], N, mode
-    pb = getattr(S, gen)(B, N=N, seed=seed)
-    try:
-        np.savez(cache, x0=pb.x0, up=pb.u_prev, cv=pb.curv, ob=pb.obs, ctx=pb.nn_ctx)
-    except OSError:
-        pass
-    return pb.x0, pb.u_prev, pb.curv, pb.obs, pb.nn_ctx, N, mode
+        arrs = [d["x0"], d["up"], d["cv"], d["ob"], d["ctx"]]
+    else:
+        pb = getattr(S, gen)(B, N=N, seed=seed)
+        arrs = [pb.x0, pb.u_prev, pb.curv, pb.obs, pb.nn_ctx]
+        try:
+            tmp = cache + ".%d.tmp.npz" % os.getpid()
+            np.savez(tmp, x0=pb.x0, up=pb.u_prev, cv=pb.curv, ob=pb.obs, ctx=pb.nn_ctx)
+            os.replace(tmp, cache)
+        except OSError:
+            pass
+    if strong:
+        lo, hi = sharding.shard_range(B, rank, world)
+        arrs = [a[lo:hi] for a in arrs]
+    return arrs[0], arrs[1], arrs[2], arrs[3], arrs[4], N, mode
 
 
 def random_mlp(hidden=(128, 128), seed=2026):
@@ -124,7 +139,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     x0, up, cv, ob, ctx, N, mode = make_problems(args.workload, 0)
-    mlp = random_mlp() if mode == "gt_mpc" else None
+    hidden = WORKLOADS[args.workload][5]
+    mlp = random_mlp(hidden) if mode == "gt_mpc" else None
     cores = os.cpu_count() or 1
     n_sample = min(len(x0), max(256, 64 * cores))
     for _ in range(args.warmup):
@@ -137,13 +153,15 @@ def run_reference(args, rank, world):
     val = conv / tsum
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True,
+        "scaling": args.scaling or WORKLOADS[args.workload][4],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "horizon": N, "mode": mode, "problems_per_step": n_sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "first %d problems of the workload per step, all host threads; the reference's "
                                    "CasADi/IPOPT solver is not installable offline, so the oracle's fp64 C restatement "
-                                   "of the same NLP is timed" % n_sample},
+                                   "of the same NLP is timed (per-solve throughput is comparable with the GPU arm's: "
+                                   "same problems, same algorithm and tolerances, same iteration cap)" % n_sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,6 +195,8 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-closed-loop", action="store_true")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="default: the workload's own (cfg4 = strong: 65536 states in total, sharded)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -198,14 +218,36 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from igt_mpc_int_b200.planner import BatchSolver
-    x0, up, cv, ob, ctx, N, mode = make_problems(args.workload, rank)
+    from igt_mpc_int_b200 import sharding
+    scaling = args.scaling or WORKLOADS[args.workload][4]
+    x0, up, cv, ob, ctx, N, mode = make_problems(args.workload, rank, world, scaling)
     B = len(x0)
-    mlp = random_mlp() if mode == "gt_mpc" else None
+    hidden = WORKLOADS[args.workload][5]
+    mlp = random_mlp(hidden) if mode == "gt_mpc" else None
     solver = BatchSolver(N=N, precision=args.precision, mlp=mlp)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     dx0, dup, dcv, dob = t(x0), t(up), t(cv), t(ob)
     dctx = t(ctx) if mode == "gt_mpc" else None
-    out = solver.solve_batch_device(dx0, dup, dcv, dob, nn_ctx=dctx)
+    # All outputs of a rank live in ONE flat buffer (x | u | cost | viol | status, iters), so that with several GPUs the
+    # solutions are gathered by one all_gather_into_tensor over NVLink (north star: "NCCL ... only to gather solutions
+    # and metrics").  Strong-scaling blocks may differ by one problem: the buffer is sized for the largest block.
+    Bmax = B
+    if world > 1:
+        bm = torch.tensor([B], device=dev)
+        dist.all_reduce(bm, op=dist.ReduceOp.MAX)
+        Bmax = int(bm.item())
+    n64 = Bmax * ((N + 1) * 7 + N * 2 + 2)
+    flat = torch.zeros(n64 + Bmax, dtype=torch.float64, device=dev)        # + Bmax doubles = 2 Bmax int32
+    o = 0
+    def view(n, shape):
+        nonlocal o
+        v = flat[o:o + n].view(shape); o += n
+        return v
+    out = dict(x=view(B * (N + 1) * 7, (B, N + 1, 7)), u=view(B * N * 2, (B, N, 2)), cost=view(B, (B,)), viol=view(B, (B,)))
+    ints = flat[n64:].view(torch.int32)
+    out["status"], out["iters"] = ints[:B], ints[Bmax:Bmax + B]
+    gathered = torch.empty((world, flat.numel()), dtype=torch.float64, device=dev) if world > 1 else None
+    solver.solve_batch_device(dx0, dup, dcv, dob, nn_ctx=dctx, out=out)
     torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -214,35 +256,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    def step():
         solver.solve_batch_device(dx0, dup, dcv, dob, nn_ctx=dctx, out=out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), flat)            # every rank ends up with every solution
+
+    for _ in range(args.warmup):
+        step()
     barrier()
 
     # ---- device-resident timing: CUDA events around every step, L2 flushed between steps ----
     l0 = solver.launches
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
-    for e0, e1 in evs:
+    for e0, em, e1 in evs:
         flush.zero_()
         e0.record()
         solver.solve_batch_device(dx0, dup, dcv, dob, nn_ctx=dctx, out=out)
+        em.record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), flat)
         e1.record()
     barrier()
     wall = time.perf_counter() - wall0
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     launches = solver.launches - l0
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    step_ms = [e0.elapsed_time(e1) for e0, em, e1 in evs]
+    solve_ms = float(sum(e0.elapsed_time(em) for e0, em, e1 in evs))
+    coll_ms = float(sum(em.elapsed_time(e1) for e0, em, e1 in evs))
     dev_ms = float(sum(step_ms))
     status = out["status"].cpu().numpy()
     iters = out["iters"].cpu().numpy()
     conv_per_step = int((status == 0).sum())
-    from igt_mpc_int_b200 import sharding
+    acc_per_step = int((status == 6).sum())
     dev_ms_max, conv_all, iters_all, B_all = sharding.reduce_counters(dev_ms, conv_per_step, iters.sum(), B, device=dev)
+    coll_ms_max, acc_all, _, _ = sharding.reduce_counters(coll_ms, acc_per_step, 0, 0, device=dev)
     value = conv_all * args.steps / (dev_ms_max * 1e-3)
+    if world > 1:      # the gathered buffer really holds every rank's statuses (checked once, outside the timed region)
+        st_all = torch.cat([gathered[r, n64:].view(torch.int32)[:B] for r in range(world)]) if scaling != "strong" else None
+        if st_all is not None:
+            assert int((st_all == 0).sum().item()) == int(conv_all), "gathered solutions do not match the reduced counters"
 
     # ---- end-to-end: host-pointer C ABI call with pinned host buffers ----
     hin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x0, up, cv, ob)]

@@ -54,18 +54,18 @@ __global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *g
     sv.compute_guess(io, p, guess + p * P.N * 2);
 }
 
-template <typename T, bool TC, bool OBCA>
+template <typename T, bool TC, bool OBCA, bool COOP = false>
 __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws, long n_slots, long B, Sched sc,
                                                                const double *guess, T *mlp_scratch, int mlp_width,
                                                                MlpTcWeights wt, int quota, int cs)
 {
-    extern __shared__ uint8_t dyn_smem[];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
     long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;   // grid is sized to n_slots exactly
     const DevParams<T> &P = ConstP<T>::get(cs);
     MlpTcCtx tc;
     if (TC) mlp_tc_setup(tc, dyn_smem, wt);
-    solve_persistent<T, TC, 32, OBCA>(P, io, ws, slot, B, sc, guess,
-                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc, quota, cs);
+    solve_persistent<T, TC, 32, OBCA, COOP>(P, io, ws, slot, B, sc, guess,
+                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc, quota, cs, dyn_smem);
     if (TC) mlp_tc_teardown(tc);
 }
 
@@ -255,6 +255,22 @@ __global__ void __launch_bounds__(128) mlp_ref_kernel(long B, const double *sN, 
     out[6 * p] = t.V; out[6 * p + 1] = t.gs; out[6 * p + 2] = t.gv; out[6 * p + 3] = t.Hss; out[6 * p + 4] = t.Hsv; out[6 * p + 5] = t.Hvv;
 }
 
+// the exact cooperative evaluation (mlp_coop.cuh) standalone: one CTA pass per 256 problems
+__global__ void __launch_bounds__(256, 1) mlp_coop_kernel(long B, const double *sN, const double *vN, const double *ctx,
+                                                          double *out, int cs)
+{
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const DevParams<double> &P = c_Pd[cs];
+    for (long base = (long)blockIdx.x * 256; base < B; base += (long)gridDim.x * 256) {
+        const long p = base + threadIdx.x;
+        const bool valid = p < B;
+        double cx[4] = { 0, 0, 0, 0 }, o[6], s = 0, v = 0;
+        if (valid) { s = sN[p]; v = vN[p]; for (int i = 0; i < 4; i++) cx[i] = ctx[4 * p + i]; }
+        mlp_coop_eval(P, dyn_smem, valid, s, v, cx, o);
+        if (valid) for (int i = 0; i < 6; i++) out[6 * p + i] = o[i];
+    }
+}
+
 // dependent-free FMA chains: the CUDA-core roofline denominator that MEASURED_PEAKS.json lacks
 template <typename T>
 __global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters)
@@ -276,7 +292,8 @@ struct igt_handle {
     DevParams<double> Pd;
     bool has_mlp = false;
     MlpTcWeights tc = {};              // tensor-core copy of the value network (6-128-128-1 only)
-    int use_tc = 1;                    // igt_set_option("tensor_core_mlp", 0) forces the CUDA-core value term
+    int use_tc = 0;                    // igt_set_option("tensor_core_mlp", 1): fp32-accurate tcgen05 value term (6-128-128-1 nets)
+    bool coop_ok = false;              // every layer <= MLP_COOP_W wide: the exact CTA-cooperative evaluation applies
     int use_small = 1;                 // igt_set_option("latency_path", 0) keeps small batches on the throughput kernel
     int mlp_width = 0;
     std::vector<void *> mlp_bufs;      // device weight buffers (both precisions)
@@ -471,7 +488,19 @@ int igt_set_mlp(igt_handle *h, int n_layers, const int *dims, const double *cons
         CK(cudaMemcpy(dbf, bf.data(), nb * 4, cudaMemcpyHostToDevice));
         h->Pd.W[l] = (const double *)dWd; h->Pd.b[l] = (const double *)dbd;
         h->Pf.W[l] = (const float *)dWf; h->Pf.b[l] = (const float *)dbf;
+        // transposed copies [in][out] for the cooperative evaluation (mlp_coop.cuh)
+        std::vector<double> wtd(nw); std::vector<float> wtf(nw);
+        for (int o = 0; o < dims[l + 1]; o++)
+            for (int i = 0; i < dims[l]; i++) { wtd[(size_t)i * dims[l + 1] + o] = W[l][(size_t)o * dims[l] + i]; wtf[(size_t)i * dims[l + 1] + o] = (float)W[l][(size_t)o * dims[l] + i]; }
+        void *dTd, *dTf;
+        CK(cudaMalloc(&dTd, nw * 8)); h->mlp_bufs.push_back(dTd);
+        CK(cudaMalloc(&dTf, nw * 4)); h->mlp_bufs.push_back(dTf);
+        CK(cudaMemcpy(dTd, wtd.data(), nw * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dTf, wtf.data(), nw * 4, cudaMemcpyHostToDevice));
+        h->Pd.Wt[l] = (const double *)dTd; h->Pf.Wt[l] = (const float *)dTf;
     }
+    h->coop_ok = true;
+    for (int l = 0; l <= n_layers; l++) if (dims[l] > MLP_COOP_W) h->coop_ok = false;
     for (int i = 0; i < 36; i++) { h->Pd.Wn[i] = Wn[i]; h->Pf.Wn[i] = (float)Wn[i]; }
     for (int i = 0; i < 6; i++) { h->Pd.mu_f[i] = mu_f[i]; h->Pf.mu_f[i] = (float)mu_f[i]; }
     h->Pd.sigma_t = sigma_t; h->Pd.mu_t = mu_t; h->Pf.sigma_t = (float)sigma_t; h->Pf.mu_t = (float)mu_t;
@@ -603,7 +632,9 @@ static int solve_dev_impl(igt_handle *h, int B, const double *x0, const double *
     long n_slots = n_cta * bs;
     rc = small ? IGT_OK : grow(h, &h->ws, &h->ws_bytes, (size_t)L.total * n_slots * esz, st);
     if (rc) return rc;
-    if (nn_ctx) {
+    const bool use_tc = nn_ctx && h->tc.enabled && h->use_tc && !obca;   // (OBCA + gt_mpc: per-thread value term)
+    const bool use_coop = nn_ctx && !use_tc && f64 && h->coop_ok && !obca;
+    if (nn_ctx && !use_tc && !use_coop) {                                 // per-thread evaluation: activations in HBM
         rc = grow(h, &h->mlp_scratch, &h->mlp_scratch_bytes, (size_t)12 * h->mlp_width * n_slots * esz, st);
         if (rc) return rc;
     }
@@ -628,7 +659,6 @@ static int solve_dev_impl(igt_handle *h, int B, const double *x0, const double *
         h->launches++;
     }
     int gs = (int)(n_slots / bs);
-    const bool use_tc = nn_ctx && h->tc.enabled && h->use_tc && !obca;   // (OBCA + gt_mpc: CUDA-core value term)
     if (small) {
         if (obca) {
             CK(cudaFuncSetAttribute(solve_small_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
@@ -648,6 +678,11 @@ static int solve_dev_impl(igt_handle *h, int B, const double *x0, const double *
             CK(cudaFuncSetAttribute(solve_kernel<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
             solve_kernel<float, true, false><<<gs, bs, TC_SMEM_BYTES, st>>>(io, (float *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota, cs);
         }
+    } else if (use_coop) {
+        // gt_mpc, exact value term: CTA-cooperative evaluation, one warp per evaluation (mlp_coop.cuh)
+        const int sm = mlp_coop_smem_bytes<double>(SOLVE_BLOCK);
+        CK(cudaFuncSetAttribute(solve_kernel<double, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        solve_kernel<double, false, false, true><<<gs, bs, sm, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota, cs);
     } else if (obca) {
         solve_kernel<double, false, true><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
                                                              nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
@@ -834,7 +869,8 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
     if (!h) return IGT_EINVAL;
     if (B < 0 || !sN || !vN || !nn_ctx || !out) { h->err = "igt_mlp_value: null argument"; return IGT_EINVAL; }
     if (!h->has_mlp) { h->err = "igt_mlp_value: igt_set_mlp was never called"; return IGT_ENOMLP; }
-    if (use_tensor_cores && !h->tc.enabled) { h->err = "igt_mlp_value: tensor-core path needs a 6-128-128-1 network"; return IGT_EINVAL; }
+    if (use_tensor_cores == 1 && !h->tc.enabled) { h->err = "igt_mlp_value: tensor-core path needs a 6-128-128-1 network"; return IGT_EINVAL; }
+    if (use_tensor_cores == 2 && !h->coop_ok) { h->err = "igt_mlp_value: the cooperative evaluation needs layers <= 128 wide"; return IGT_EINVAL; }
     if (B == 0) return IGT_OK;
     std::lock_guard<std::mutex> lk(h->mu);
     int cs = 0;
@@ -847,7 +883,15 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
     CK(cudaMemcpy(ds, sN, nb * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dv, vN, nb * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dc, nn_ctx, nb * 32, cudaMemcpyHostToDevice));
-    if (use_tensor_cores) {
+    if (use_tensor_cores == 2) {
+        rc = acquire_cslot(h, 1, nullptr, &cs);
+        if (rc) return rc;
+        int grid = (int)((nb + 255) / 256);
+        if (grid > h->n_sm) grid = h->n_sm;
+        const int sm = mlp_coop_smem_bytes<double>(256);
+        CK(cudaFuncSetAttribute(mlp_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        mlp_coop_kernel<<<grid, 256, sm>>>(B, ds, dv, dc, dout, cs);
+    } else if (use_tensor_cores) {
         int grid = (int)((nb + 255) / 256);
         if (grid > h->n_sm) grid = h->n_sm;
         mlp_tc_kernel<<<grid, 256, TC_SMEM_BYTES>>>(h->tc, B, ds, dv, dc, dout);
@@ -860,7 +904,7 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
     }
     h->launches++;
     CK(cudaGetLastError());
-    rc = end_call(h, nullptr, use_tensor_cores ? 0 : 2);
+    rc = end_call(h, nullptr, use_tensor_cores == 1 ? 0 : 2);
     if (rc) return rc;
     CK(cudaMemcpy(out, dout, nb * 48, cudaMemcpyDeviceToHost));
     return IGT_OK;

@@ -21,6 +21,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <type_traits>
 #include "mlp_tc.cuh"
 #include "obca.cuh"
 
@@ -75,7 +76,12 @@ struct DevParams {
     T cinf_A[MAX_CINF][2], cinf_b[MAX_CINF];
     T Wn[36], mu_f[6], sigma_t, mu_t;
     const T *W[MAX_MLP_LAYERS], *b[MAX_MLP_LAYERS];   // device pointers, row-major [out][in]
+    const T *Wt[MAX_MLP_LAYERS];                      // the same weights transposed, [in][out] (mlp_coop.cuh)
 };
+
+}  // namespace igt
+#include "mlp_coop.cuh"
+namespace igt {
 
 // ------------------------------------------------------------------ workspace ----------
 // Row bookkeeping: stage 0 carries the 8 input rows; stage k >= 1 carries 5 state rows
@@ -1797,16 +1803,18 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
 // gt_mpc with the tensor-core value term: the terminal values (and derivatives) of all n * n_spec
 // line-search candidates of the CTA in one CTA-wide evaluation -- thread t takes candidate t / n of the
 // t % n-th listed problem -- left in Tc(candidate buffer, 2..7) for the owner's accept_trials.
-template <typename T>
-__device__ __forceinline__ void tc_candidates(const DevParams<T> &P, const ProbIO &io, T *ws_base, const WsLayout &L,
-                                              const NodeList<T> &nl, int n, int n_spec, MlpTcCtx &tc)
+// COOP: the same with the exact cooperative evaluation (mlp_coop.cuh) instead of the tensor cores.
+template <typename T, bool COOP, typename WS>
+__device__ __forceinline__ void tc_candidates(const DevParams<T> &P, const ProbIO &io, T *ws_base, const WS &wproto,
+                                              const NodeList<T> &nl, int n, int n_spec, MlpTcCtx *tc, uint8_t *coop_smem)
 {
     if (n == 0) return;                                            // CTA-uniform
     const int t = threadIdx.x, q = t % n, j = t / n;
     bool valid = t < n * n_spec && j < P.n_alpha - nl.ctx[q].ls;
-    Ws<T> w; w.L = L;
+    WS w = wproto;
     int nb = 0;
-    float cx[4] = { 0.f, 0.f, 0.f, 0.f }, o[6], sN = 0.f, vN = 0.f;
+    using V = typename std::conditional<COOP, T, float>::type;
+    V cx[4] = { V(0), V(0), V(0), V(0) }, o[6], sN = V(0), vN = V(0);
     if (valid) {
         w.bind(ws_base, nl.slot[q]);
         nb = cand_buf(nl.ctx[q].cur, j);
@@ -1815,11 +1823,12 @@ __device__ __forceinline__ void tc_candidates(const DevParams<T> &P, const ProbI
     if (valid) {
         const long p = (nl.ctx[q].x0p - io.x0) / NZ;
 #pragma unroll
-        for (int i = 0; i < 4; i++) cx[i] = float(io.ctx[p * 4 + i]);
-        sN = float(w.Z(nb, P.N, IS)); vN = float(w.Z(nb, P.N, IV));
+        for (int i = 0; i < 4; i++) cx[i] = V(io.ctx[p * 4 + i]);
+        sN = V(w.Z(nb, P.N, IS)); vN = V(w.Z(nb, P.N, IV));
     }
     if (__syncthreads_or(valid)) {
-        mlp_tc_eval(tc, valid, sN, vN, cx, o);
+        if constexpr (COOP) mlp_coop_eval(P, coop_smem, valid, sN, vN, cx, o);
+        else mlp_tc_eval(*tc, valid, sN, vN, cx, o);
         if (valid) {
 #pragma unroll
             for (int i = 0; i < 6; i++) w.Tc(nb, 2 + i) = T(o[i]);
@@ -1840,11 +1849,11 @@ __device__ int g_round_ph[512][12];      // per loop pass: kcycles per phase
 #define IGT_TICK(i) do { } while (0)
 #endif
 
-template <typename T, bool TC, int STRIDE = 32, bool OBCA = false>
+template <typename T, bool TC, int STRIDE = 32, bool OBCA = false, bool COOP = false>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
                                                  long slot, long B, const Sched &sc,
                                                  const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc,
-                                                 int quota, int cslot)
+                                                 int quota, int cslot, uint8_t *coop_smem = nullptr)
 {
     __shared__ NodeList<T> nl;
     if (threadIdx.x == 0) nl.cslot = cslot;                     // (the first CTA barrier of the loop publishes it)
@@ -1859,6 +1868,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
     long p = -1;
     const long bound = slot;
     if (TC) sv.phi_noise = T(3e-7);
+    constexpr bool CTA_MLP = TC || COOP;                          // value term evaluated CTA-wide at the two uniform points below
 #ifdef IGT_PHASE_CLOCKS
     const bool clk_on = blockIdx.x == 0 && threadIdx.x == 0;
     long long clk[16] = { 0 }, clk_t = clock64(), round_t = clk_t;
@@ -1877,7 +1887,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
             else {
                 const double *u_src = (io.u_init ? io.u_init : guess) + p * P.N * 2;
                 if (sv.init(io, p, io.ctx != nullptr, u_src, io.u_init != nullptr)) {
-                    if (!TC) sv.terminal_of(sv.cur, sv.tcur, true);
+                    if (!CTA_MLP) sv.terminal_of(sv.cur, sv.tcur, true);
                     active = true;
                     fresh = true;
                 } else {
@@ -1891,6 +1901,15 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
                 float sN = fresh ? float(sv.w.Z(sv.cur, P.N, IS)) : 0.f, vN = fresh ? float(sv.w.Z(sv.cur, P.N, IV)) : 0.f;
                 mlp_tc_eval(*tc, fresh, sN, vN, cx, o);
                 if (fresh) term_from_tc(o, sv.tcur);
+            }
+        }
+        if (COOP) {
+            const bool want = fresh && sv.gt;
+            if (__syncthreads_or(want)) {
+                T o[6];
+                const T sN = want ? sv.w.Z(sv.cur, P.N, IS) : T(0), vN = want ? sv.w.Z(sv.cur, P.N, IV) : T(0);
+                mlp_coop_eval(P, coop_smem, want, sN, vN, sv.ctx, o);
+                if (want) { sv.tcur.V = o[0]; sv.tcur.gs = o[1]; sv.tcur.gv = o[2]; sv.tcur.Hss = o[3]; sv.tcur.Hsv = o[4]; sv.tcur.Hvv = o[5]; }
             }
         }
         // a warp is finished once its lanes can fetch no more and none of them is busy
@@ -1940,10 +1959,10 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         if (clk_on) { long long m_ = g_mid_t; clk[7] += m_ - clk_t; if (round_i < 512) g_round_ph[round_i][7] += (int)((m_ - clk_t) >> 10); clk_t = m_; }
 #endif
         IGT_TICK(11);
-        if (TC) tc_candidates(P, io, ws_base, sv.w.L, nl, n_try, n_spec, *tc);   // value terms of all candidates, CTA-wide
+        if (CTA_MLP) tc_candidates<T, COOP>(P, io, ws_base, sv.w, nl, n_try, n_spec, tc, coop_smem);   // value terms of all candidates, CTA-wide
         if (trying) {
             const int left = P.n_alpha - sv.ls;
-            sv.accept_trials(n_spec < left ? n_spec : left, TC);
+            sv.accept_trials(n_spec < left ? n_spec : left, CTA_MLP);
         }
         IGT_TICK(8);
         if (active && sv.done) { sv.write_out(io, p); active = false; }

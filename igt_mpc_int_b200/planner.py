@@ -124,11 +124,12 @@ class BatchSolver:
         self._check(self.lib.igt_set_option(self._h, name.encode(), float(value)), "igt_set_option")
 
     def mlp_value(self, sN, vN, nn_ctx, tensor_cores=True):
-        """Value term and its (s_N, v_N) derivatives: out[B,6] = (V, Vs, Vv, Vss, Vsv, Vvv)."""
+        """Value term and its (s_N, v_N) derivatives: out[B,6] = (V, Vs, Vv, Vss, Vsv, Vvv).
+        tensor_cores: True / 1 tcgen05 kernel, False / 0 per-thread fp64, 2 the solver's cooperative fp64 evaluation."""
         sN = _f64(sN).ravel(); B = sN.shape[0]
         vN = _f64(vN, (B,)); nn_ctx = _f64(nn_ctx, (B, 4))
         out = np.empty((B, 6))
-        rc = self.lib.igt_mlp_value_host(self._h, B, _hp(sN), _hp(vN), _hp(nn_ctx), _hp(out), 1 if tensor_cores else 0)
+        rc = self.lib.igt_mlp_value_host(self._h, B, _hp(sN), _hp(vN), _hp(nn_ctx), _hp(out), int(tensor_cores))
         self._check(rc, "igt_mlp_value_host")
         return out
 

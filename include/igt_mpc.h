@@ -163,12 +163,17 @@ long long igt_launch_count(const igt_handle *h);
 
 /* The gt_mpc value term alone (mpc.py:367-369, model.py:53-67): V(W (x_N - mu_f)) sigma_t + mu_t and its
  * first / second derivatives in (s_N, v_N), out[B,6] = (V, dV/ds, dV/dv, d2V/dss, d2V/dsv, d2V/dvv).
- * use_tensor_cores = 1: tcgen05 kernel (6-128-128-1 networks); 0: fp64 CUDA-core kernel.  Host fp64 arrays. */
+ * use_tensor_cores = 1: tcgen05 kernel (6-128-128-1 networks); 0: fp64 per-thread kernel; 2: the exact fp64
+ * CTA-cooperative evaluation the solver uses (csrc/mlp_coop.cuh; any network with layers <= 128 wide).  Host fp64 arrays. */
 int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN, const double *nn_ctx,
                        double *out, int use_tensor_cores);
 
-/* Run-time switches.  "tensor_core_mlp" (default 1): evaluate the gt_mpc value term of 6-128-128-1 networks
- * with the tcgen05 kernel inside the solver; 0 = fp64 CUDA-core evaluation (always used for other shapes).
+/* Run-time switches.
+ * "tensor_core_mlp" (default 0).  The gt_mpc value term is evaluated exactly (fp64) by default, CTA-cooperatively
+ * (csrc/mlp_coop.cuh: one warp per evaluation, any network up to 128 wide -- all eight shipped V_GT_sc*.pt).  1 = the
+ * tcgen05 kernel (csrc/mlp_tc.cuh; 6-128-128-1 networks, bf16x3 = fp32-accurate): measured no faster than the exact
+ * path on a B200 and it perturbs the merit at 1e-7, so closed-loop outcomes can differ from the
+ * fp64 oracle's; kept as an option.
  * "latency_path" (default 1): 'mpc'-mode batches of at most one problem per SM (a closed-loop step solves the two
  * vehicles of an episode) run one CTA per problem with the workspace in shared memory; 0 = throughput kernel. */
 int igt_set_option(igt_handle *h, const char *name, double value);

@@ -66,15 +66,17 @@ def test_gt_mpc_solve_matches_oracle(oracle_params, hidden):
     r = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, nn_ctx=pb.nn_ctx)
     o = c_oracle.COracle(oracle_params[N], term, max_iter=s.params.max_iter, max_trials=s.params.max_trials).solve(pb.x0, pb.u_prev, pb.curv, pb.obs,
                                                                                   nn_ctx=pb.nn_ctx)
+    # default: the exact (fp64, CTA-cooperative) value term -- north-star tolerances on EVERY converged problem
     ok = (r["status"] == 0) & (o["status"] == 0)
     assert ok.sum() > 0.7 * B
-    assert np.mean((r["status"] == 0) == (o["status"] == 0)) > 0.97
-    assert np.quantile(relerr(r["cost"][ok], o["cost"][ok]), 0.98) < 1e-4
-    assert np.quantile(np.abs(r["u"][ok] - o["U"][ok]).reshape(ok.sum(), -1).max(1), 0.98) < 1e-3
+    assert np.mean(r["status"] == o["status"]) > 0.98
+    assert np.max(relerr(r["cost"][ok], o["cost"][ok])) < 1e-4
+    assert np.max(np.abs(r["u"][ok] - o["U"][ok])) < 1e-3
     assert np.max(r["viol"][ok]) <= 1e-6
     if hidden == (128, 128):
-        # the same solve with the tensor-core value term switched off (fp64 CUDA cores): same outcomes
-        s.set_option("tensor_core_mlp", 0)
+        # the optional tensor-core value term (fp32-accurate): same optima within the tolerances for all but the few
+        # problems whose line search it steers elsewhere (documented in igt_mpc.h: not the parity path)
+        s.set_option("tensor_core_mlp", 1)
         r2 = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, nn_ctx=pb.nn_ctx)
         ok2 = (r2["status"] == 0) & (r["status"] == 0)
         assert np.mean((r2["status"] == 0) == (r["status"] == 0)) > 0.97
@@ -83,10 +85,10 @@ def test_gt_mpc_solve_matches_oracle(oracle_params, hidden):
 
 
 def test_gt_mpc_full_size_batch_properties():
-    """BASELINE config 3 at full size (gt_mpc, 16384 problems, random-init 6-128-128-1 network, tensor-core value
+    """BASELINE config 3 at full size (gt_mpc, 16384 problems, random-init 6-128-128-1 network, exact cooperative value
     term with the speculative line search): rows satisfied to 1e-6, cost reproduced by the fp64 evaluation kernel
-    to the accuracy of the fp32-accurate value term, and bit-identical results for the reversed batch (which
-    candidate lands in which tensor-core row depends on the batch; the result of a row does not)."""
+    to round-off, and bit-identical results for the reversed batch (which warp evaluates which candidate depends on
+    the batch; the result does not)."""
     from igt_mpc_int_b200.planner import BatchSolver
     from igt_mpc_int_b200 import scenarios as S
     term = _term(_net((128, 128)), False)
@@ -99,7 +101,7 @@ def test_gt_mpc_full_size_batch_properties():
     assert np.max(r["viol"][ok]) <= 1e-6
     idx = np.where(ok)[0][::16]
     ev = s.evaluate(pb.x0[idx], pb.u_prev[idx], pb.curv[idx], pb.obs[idx], r["u"][idx], nn_ctx=pb.nn_ctx[idx])
-    assert np.max(relerr(ev["cost"], r["cost"][idx])) < 2e-5 and np.max(ev["viol"]) <= 1e-6
+    assert np.max(relerr(ev["cost"], r["cost"][idx])) < 1e-10 and np.max(ev["viol"]) <= 1e-6
     rr = s.solve_batch(pb.x0[::-1], pb.u_prev[::-1], pb.curv[::-1], pb.obs[::-1], nn_ctx=pb.nn_ctx[::-1])
     for k in ("status", "iters", "cost", "u"):
         assert np.array_equal(rr[k][::-1], r[k], equal_nan=True), k

@@ -9,8 +9,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 pb = S.mid_episode(B, N=40, seed=2026)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 x0, up, cv, ob, ctx = t(pb.x0), t(pb.u_prev), t(pb.curv), t(pb.obs), t(pb.nn_ctx)
-mlp = bench.random_mlp()
-for name, use_ctx, tcflag in (("mpc", False, 1), ("gt_tc", True, 1), ("gt_cc", True, 0)):
+HID = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (128, 128)
+mlp = bench.random_mlp(HID)
+for name, use_ctx, tcflag in (("mpc", False, 1), ("gt_tc", True, 1), ("gt_coop", True, 0)):
     s = BatchSolver(N=40, mlp=mlp)
     s.set_option("tensor_core_mlp", tcflag)
     out = s.solve_batch_device(x0, up, cv, ob, nn_ctx=ctx if use_ctx else None); torch.cuda.synchronize()
