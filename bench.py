@@ -326,7 +326,7 @@ def main():
 
     # ---- p50 per-step solve latency of a closed-loop episode (second half of BASELINE.json's metric):
     #      scenario 1, both vehicles per step (B = 2), 150 steps, host to host through solve_batch ----
-    cl_p50 = cl_p90 = None
+    cl_p50 = cl_p90 = cl_cpu_p50 = cl_cpu_p90 = None
     if rank == 0 and mode == "mpc" and not args.no_closed_loop:
         from igt_mpc_int_b200 import episode
         spec = episode.reference_episode_specs(scenarios=[1])[:1]
@@ -335,6 +335,10 @@ def main():
         cl_p50, cl_p90 = float(np.percentile(res.step_latency_ms, 50)), float(np.percentile(res.step_latency_ms, 90))
         if cl_solver is not solver:
             cl_solver.close()
+        if not args.no_cpu_baseline:        # the same episode with the oracle's C port as the solver (2 host threads: one per vehicle)
+            from tests.oracle_backend import OracleBackend
+            ro = episode.run_closed_loop(OracleBackend(N=40, max_iter=MAX_ITER_DEFAULT), spec, steps=150, N=40, record_latency=True)
+            cl_cpu_p50, cl_cpu_p90 = float(np.percentile(ro.step_latency_ms, 50)), float(np.percentile(ro.step_latency_ms, 90))
 
     if rank == 0:
         # ---- rooflines ----
@@ -346,6 +350,7 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         traffic = traffic_gbs = None                          # dram bytes per launch from the committed ncu capture
+        tr = {}
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if tr.get("workload") == args.workload and tr.get("precision") == args.precision:
@@ -353,37 +358,61 @@ def main():
                 traffic_gbs = traffic / (tr["launch_ms_under_ncu"] * 1e-3) / 1e9
         except Exception:
             pass
-        kernel_ms = dev_ms / args.steps                       # solver + guess kernels of one step on this rank
+        kernel_ms = solve_ms / args.steps                     # solver + guess kernels of one step on this rank
         alg_bytes = 8.0 * (11 * N + 24) * B                   # 4(11N+24) B/solve for fp32 I/O; ours is fp64
         achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        alg_flops = float(iters.sum()) * N * 1.4e4            # 1.4e4 FLOP per stage-iteration
+        stage_iters = float(iters.sum()) * N
+        alg_flops = stage_iters * 1.4e4                       # 1.4e4 FLOP per stage-iteration
         fma_peak = solver.measure_fma_peak()
+        # measured fp64 work: thread-level DFMA / DADD / DMUL of the solver kernel counted by ncu in the committed
+        # capture (profiles/traffic.json), scaled by this run's stage-iterations
+        meas_flops = None
+        try:
+            if tr.get("workload") == args.workload and tr.get("precision") == args.precision and "fp64_flop_per_stage_iter" in tr:
+                meas_flops = stage_iters * float(tr["fp64_flop_per_stage_iter"])
+        except Exception:
+            pass
+        roof_flops = meas_flops if meas_flops is not None else alg_flops
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": args.workload, "horizon": N, "mode": mode, "problems_per_gpu_per_step": B,
+            "config": {"workload": args.workload, "horizon": N, "mode": mode,
+                       "problems_per_gpu_per_step": B, "problems_per_step_all_gpus": int(B_all),
                        "l2": "flushed (256 MiB memset) between timed steps", "warm_start": False,
-                       "parallelism": "dp%d (independent problems, no data-path collective)" % world},
+                       "value_network": None if hidden is None else "6-" + "-".join(str(h) for h in hidden) + "-1 random init, exact fp64 value term",
+                       "parallelism": "dp%d: independent problems, contiguous block per rank; %s" % (
+                           world, "one all_gather_into_tensor of every rank's solutions per step inside the timed region"
+                           if world > 1 else "single GPU")},
             "converged_fraction": conv_all / B_all, "mean_iterations": iters_all / B_all,
+            "ipopt_band": {"acceptable_per_step": int(acc_all), "fraction": acc_all / B_all,
+                           "what": "solves that failed the tight tolerances (1e-6 / 1e-8 / 1e-7) but stopped at a point inside the "
+                                   "reference's own IPOPT tolerances (mpc.py:133-135, tol 1e-3; status 6): NOT counted in value"},
             "p50_step_latency_ms": float(np.median(step_ms)), "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
-            "closed_loop_step_latency_ms": {"p50": cl_p50, "p90": cl_p90,
+            "solve_ms_per_step": solve_ms / args.steps,
+            "collective_ms_per_step": coll_ms_max / args.steps if world > 1 else 0.0,
+            "gathered_bytes_per_step": int(flat.numel() * 8 * world) if world > 1 else 0,
+            "closed_loop_step_latency_ms": {"p50": cl_p50, "p90": cl_p90, "cpu_p50": cl_cpu_p50, "cpu_p90": cl_cpu_p90,
                                             "what": "scenario 1 episode, 150 steps, one B=2 solve per step (both vehicles), "
-                                                    "host to host incl. H2D/D2H, warm-started after step 0"},
+                                                    "host to host incl. H2D/D2H, warm-started after step 0; cpu_* = the same "
+                                                    "episode with the oracle's fp64 C port as the solver on the host"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
-                         "traffic_gbs": traffic_gbs, "traffic_frac": None if traffic_gbs is None else traffic_gbs / hbm_peak,
-                         "note": "achieved = algorithmic bytes 8*(11N+24) per solve / kernel time; traffic = DRAM bytes of "
-                                 "the solver kernel in the committed ncu capture (its per-problem workspace streams "
-                                 "through HBM in every phase of every iteration: traffic_gbs / peak is the bandwidth "
-                                 "actually drawn), see also compute_roofline (SURVEY 8(d))"},
-            "compute_roofline": {"bound": "%s-fma" % args.precision, "achieved": alg_flops / (kernel_ms * 1e-3) / 1e12,
-                                 "peak": fma_peak, "unit": "TFLOP/s",
-                                 "frac": alg_flops / (kernel_ms * 1e-3) / 1e12 / fma_peak,
-                                 "note": "algorithmic 1.4e4 FLOP per stage-iteration x measured iterations; peak = "
-                                         "dependent-free FMA chains measured on this GPU in this run"},
+            # the binding roofline of this path is the FP64 CUDA-core pipe, not HBM bytes
+            "roofline": {"bound": "fp64-fma", "achieved": roof_flops / (kernel_ms * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
+                         "frac": roof_flops / (kernel_ms * 1e-3) / 1e12 / fma_peak, "traffic": traffic,
+                         "flops_source": "ncu-counted DFMA x2 + DADD + DMUL thread instructions per stage-iteration (profiles/traffic.json) x "
+                                         "this run's stage-iterations" if meas_flops is not None else
+                                         "SURVEY 8(d) estimate 1.4e4 FLOP per stage-iteration x this run's stage-iterations",
+                         "peak_source": "dependent-free fp64 FMA chains measured on this GPU in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                         "algorithmic_frac": alg_flops / (kernel_ms * 1e-3) / 1e12 / fma_peak},
+            "hbm_traffic": {"bound": "hbm", "algorithmic_gbs": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                            "algorithmic_frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
+                            "dram_bytes_per_launch": traffic, "drawn_gbs": traffic_gbs,
+                            "drawn_frac": None if traffic_gbs is None else traffic_gbs / hbm_peak,
+                            "wasted_ratio": None if traffic is None else traffic / alg_bytes,
+                            "note": "algorithmic = 8*(11N+24) bytes per solve; dram_bytes = dram__bytes_read + write of the solver "
+                                    "kernel (ncu, committed capture): the per-problem workspace streams through HBM in every phase"},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
@@ -391,7 +420,11 @@ def main():
             n_sample = min(B, max(512, 128 * cores))
             c, dt = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n_sample, solver.params.max_iter,
                                  max_trials=solver.params.max_trials, ctx=ctx)
+            n1 = min(B, 192)
+            c1, dt1 = cpu_baseline(x0, up, cv, ob, N, mode, mlp, n1, solver.params.max_iter, threads=1,
+                                   max_trials=solver.params.max_trials, ctx=ctx)
             line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "single_core_value": c1 / dt1, "single_core_sample": "first %d problems, 1 thread" % n1,
                                     "sample": "first %d problems of the same batch, oracle fp64 C restatement on all "
                                               "host threads (the reference's CasADi/IPOPT solver is not installable "
                                               "offline)" % n_sample}

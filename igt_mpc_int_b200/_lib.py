@@ -65,7 +65,8 @@ _lib = None
 
 EXPORTS = ("igt_version", "igt_default_params", "igt_create", "igt_destroy", "igt_last_error",
            "igt_set_mlp", "igt_rollout_dev", "igt_rollout_host", "igt_eval_host", "igt_solve_dev",
-           "igt_solve_host", "igt_launch_count", "igt_measure_fma_peak", "igt_mlp_value_host", "igt_set_option")
+           "igt_solve_host", "igt_launch_count", "igt_measure_fma_peak", "igt_mlp_value_host", "igt_set_option",
+           "igt_episode_run_host")
 
 
 def load():
@@ -99,6 +100,8 @@ def load():
     lib.igt_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     lib.igt_set_option.restype = C.c_int
     lib.igt_launch_count.restype = C.c_longlong
+    lib.igt_episode_run_host.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [vp] * 9
+    lib.igt_episode_run_host.restype = C.c_int
     for f in ("igt_default_params", "igt_create", "igt_set_mlp", "igt_rollout_dev", "igt_rollout_host",
               "igt_eval_host", "igt_solve_dev", "igt_solve_host"):
         getattr(lib, f).restype = C.c_int

@@ -41,6 +41,7 @@ static_assert(N_CSLOTS * (sizeof(DevParams<float>) + sizeof(DevParams<double>)) 
 
 template <> struct igt::ConstP<float> { static __device__ __forceinline__ const DevParams<float> &get(int s) { return c_Pf[s]; } };
 template <> struct igt::ConstP<double> { static __device__ __forceinline__ const DevParams<double> &get(int s) { return c_Pd[s]; } };
+#include "episode.cuh"
 
 // ------------------------------------------------------------------ kernels -------------
 // cold-start guess: best of five tracking-controller rollouts per problem -> guess[B][N][2]
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *g
 {
     long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
+    if (io.u_init && (!io.warm || io.warm[p])) return;            // warm-started problem: no cold-start guess needed
     const DevParams<T> &P = ConstP<T>::get(cs);
     Solver<T, Ws<T, 32, OBCA>> sv(P);
     sv.compute_guess(io, p, guess + p * P.N * 2);
@@ -301,6 +303,7 @@ struct igt_handle {
     void *mlp_scratch = nullptr; size_t mlp_scratch_bytes = 0;
     void *stage = nullptr; size_t stage_bytes = 0;     // device staging for *_host calls
     void *guess = nullptr; size_t guess_bytes = 0;     // cold-start controls [B][N][2] + the work counter
+    void *episode = nullptr; size_t episode_bytes = 0; // igt_episode_run_host: state, records, solver inputs / outputs
     int n_sm = 0;
     long long launches = 0;
     std::string err;
@@ -448,6 +451,7 @@ void igt_destroy(igt_handle *h)
     if (h->mlp_scratch) cudaFree(h->mlp_scratch);
     if (h->stage) cudaFree(h->stage);
     if (h->guess) cudaFree(h->guess);
+    if (h->episode) cudaFree(h->episode);
     delete h;
 }
 
@@ -604,7 +608,8 @@ int igt_rollout_host(igt_handle *h, int B, const float *z0, const float *u, cons
 
 static int solve_dev_impl(igt_handle *h, int B, const double *x0, const double *u_prev, const double *curv,
                           const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u_init,
-                          double *x, double *u, double *cost, double *viol, int *status, int *iters, cudaStream_t st)
+                          double *x, double *u, double *cost, double *viol, int *status, int *iters, cudaStream_t st,
+                          const int *warm = nullptr)
 {
     if (B < 0 || !x0 || !u_prev || !curv || !obs_xy || !x || !u || !cost || !viol || !status || !iters) {
         h->err = "igt_solve: null argument"; return IGT_EINVAL;
@@ -651,7 +656,8 @@ static int solve_dev_impl(igt_handle *h, int B, const double *x0, const double *
     CK(cudaMemsetAsync(sb, 0, 256, st));
     ProbIO io = { x0, u_prev, curv, obs_xy, nn_ctx, u_init, x, u, cost, viol, status, iters };
     io.obs_psi = obs_psi;
-    if (!u_init) {
+    io.warm = warm;
+    if (!u_init || warm) {
         int gbs = 128, ggs = (B + gbs - 1) / gbs;
         if (obca) guess_kernel<double, true><<<ggs, gbs, 0, st>>>(io, B, guess, cs);
         else if (f64) guess_kernel<double, false><<<ggs, gbs, 0, st>>>(io, B, guess, cs);
@@ -936,6 +942,85 @@ int igt_debug_round_phases(igt_handle *h, int *ph512x12)
     return IGT_OK;
 }
 #endif
+
+int igt_episode_run_host(igt_handle *h, int E, int steps, int gt_mpc, const double *route_desc, const double *curv,
+                         const double *z0, const double *u_prev0, const double *enc, double *z_cl, double *u_cl,
+                         int *solved, float *step_ms)
+{
+    if (!h) return IGT_EINVAL;
+    if (E < 0 || steps < 1 || !route_desc || !curv || !z0 || !u_prev0 || !enc || !z_cl || !u_cl || !solved) {
+        h->err = "igt_episode_run: bad argument"; return IGT_EINVAL;
+    }
+    if (h->prm.precision != IGT_PREC_F64) { h->err = "igt_episode_run: needs precision f64"; return IGT_EINVAL; }
+    if (gt_mpc && !h->has_mlp) { h->err = "igt_episode_run: gt_mpc needs igt_set_mlp"; return IGT_ENOMLP; }
+    if (E == 0) return IGT_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (!h->hstream) CK(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    cudaStream_t st = h->hstream;
+    int rc = begin_call(h, st);
+    if (rc) return rc;
+    const int N = h->prm.N, B = 2 * E, T = steps;
+    const size_t nb = (size_t)B;
+    // one device block: state, records, solver inputs and two sets of solver outputs (the plans of t and t-1)
+    const size_t n_z = nb * 7, n_up = nb * 2, n_cv = nb * 3, n_rd = nb * ROUTE_DESC, n_en = nb, n_obs = nb * (N + 1) * 2,
+                 n_ctx = nb * 4, n_ui = nb * N * 2, n_zcl = nb * (T + 1) * 7, n_ucl = nb * T * 2, n_x = nb * (N + 1) * 7,
+                 n_u = nb * N * 2;
+    const size_t n_dbl = n_z + n_up + n_cv + n_rd + n_en + n_obs + n_ctx + n_ui + n_zcl + n_ucl + 2 * (n_x + n_u + 2 * nb);
+    const size_t n_int = nb /*warm*/ + nb /*prev_ok*/ + nb * T /*solved*/ + 2 * 2 * nb /*status, iters x2*/;
+    rc = grow(h, &h->episode, &h->episode_bytes, n_dbl * 8 + n_int * 4, st);
+    if (rc) return rc;
+    double *d = (double *)h->episode;
+    EpisodeBufs eb;
+    eb.z = d; d += n_z; eb.u_prev = d; d += n_up;
+    double *dcv = d; d += n_cv; double *drd = d; d += n_rd; double *den = d; d += n_en;
+    eb.curv = dcv; eb.rd = drd; eb.enc = den;
+    eb.obs = d; d += n_obs; eb.ctx = d; d += n_ctx; eb.u_init = d; d += n_ui;
+    eb.z_cl = d; d += n_zcl; eb.u_cl = d; d += n_ucl;
+    double *px[2], *pu[2], *pcost[2], *pviol[2];
+    for (int i = 0; i < 2; i++) { px[i] = d; d += n_x; pu[i] = d; d += n_u; pcost[i] = d; d += nb; pviol[i] = d; d += nb; }
+    int *ip = (int *)d;
+    eb.warm = ip; ip += nb; eb.prev_ok = ip; ip += nb; eb.solved = ip; ip += nb * T;
+    int *pst[2], *pit[2];
+    for (int i = 0; i < 2; i++) { pst[i] = ip; ip += nb; pit[i] = ip; ip += nb; }
+    CK(cudaMemcpyAsync(eb.z, z0, n_z * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(eb.u_prev, u_prev0, n_up * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dcv, curv, n_cv * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(drd, route_desc, n_rd * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(den, enc, n_en * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(eb.prev_ok, 0, nb * 4, st));
+    // z_cl[:, :, 0] = z0
+    CK(cudaMemcpy2DAsync(eb.z_cl, (size_t)(T + 1) * 7 * 8, eb.z, 7 * 8, 7 * 8, nb, cudaMemcpyDeviceToDevice, st));
+    std::vector<cudaEvent_t> ev;
+    if (step_ms) { ev.resize(T + 1); for (auto &e : ev) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], st)); }
+    const int bs = 128, gs = (B + bs - 1) / bs;
+    int cs = 0;
+    for (int t = 0; t < T; t++) {
+        const int cur = t & 1, prv = cur ^ 1;
+        episode_pre_kernel<<<gs, bs, 0, st>>>(eb, B, N, h->prm.dt, t, gt_mpc, px[prv], pu[prv]);
+        h->launches++;
+        rc = solve_dev_impl(h, B, eb.z, eb.u_prev, eb.curv, eb.obs, nullptr, gt_mpc ? eb.ctx : nullptr, eb.u_init, px[cur], pu[cur],
+                            pcost[cur], pviol[cur], pst[cur], pit[cur], st, eb.warm);
+        if (rc) return rc;
+        rc = acquire_cslot(h, 1, st, &cs);
+        if (rc) return rc;
+        episode_post_kernel<<<gs, bs, 0, st>>>(eb, B, N, T, t, h->prm.a_min, px[cur], pu[cur], pst[cur], cs);
+        h->launches++;
+        if (step_ms) CK(cudaEventRecord(ev[t + 1], st));
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(z_cl, eb.z_cl, n_zcl * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(u_cl, eb.u_cl, n_ucl * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(solved, eb.solved, nb * T * 4, cudaMemcpyDeviceToHost, st));
+    rc = end_call(h, st, 2);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    if (step_ms) {
+        for (int t = 0; t < T; t++) CK(cudaEventElapsedTime(&step_ms[t], ev[t], ev[t + 1]));
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    return IGT_OK;
+}
 
 int igt_set_option(igt_handle *h, const char *name, double value)
 {

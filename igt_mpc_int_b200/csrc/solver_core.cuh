@@ -167,6 +167,7 @@ struct ProbIO {
     double *x, *u, *cost, *viol;
     int *status, *iters;
     const double *obs_psi = nullptr;                         // [B,N+1] obstacle heading forecast: OBCA collision rows
+    const int *warm = nullptr;                               // [B] per-problem warm-start flags (with u_init); null: all warm
 };
 
 // ------------------------------------------------------------------ dynamics -----------
@@ -1885,8 +1886,9 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
             p = (long)atomicAdd(sc.counter, 1ULL);
             if (p >= B) exhausted = true;
             else {
-                const double *u_src = (io.u_init ? io.u_init : guess) + p * P.N * 2;
-                if (sv.init(io, p, io.ctx != nullptr, u_src, io.u_init != nullptr)) {
+                const bool warm = io.u_init && (!io.warm || io.warm[p]);
+                const double *u_src = (warm ? io.u_init : guess) + p * P.N * 2;
+                if (sv.init(io, p, io.ctx != nullptr, u_src, warm)) {
                     if (!CTA_MLP) sv.terminal_of(sv.cur, sv.tcur, true);
                     active = true;
                     fresh = true;

@@ -187,3 +187,39 @@ def run_closed_loop(solver, specs, steps=150, N=40, dt=0.1, d_min=5.6, record_la
     return EpisodeResult(z_cl=z_cl, u_cl=u_cl, solved=solved, deadlock=np.sum(final_s <= 30, axis=1) >= 2,
                          collision=dist.min(axis=1) < d_min - 1e-6, goal=final_s > 30,
                          num_infeasible=(~solved).sum(axis=2), min_distance=dist.min(axis=1), step_latency_ms=lat)
+
+
+def run_closed_loop_device(solver, specs, steps=150, N=40, d_min=5.6, mode="mpc", record_latency=False):
+    """The same closed loop with the per-timestep glue on the GPU (csrc/episode.cuh, igt_episode_run_host): all E
+    episodes advance `steps` steps without the host in the loop -- per step one glue kernel, one batched solve of all 2E
+    vehicles (per-problem warm / cold start), one plant kernel.  `solver` is a planner.BatchSolver (fp64) with horizon N.
+    Returns an EpisodeResult; step_latency_ms = device time per step (all episodes together)."""
+    import ctypes as C
+    assert mode in ("mpc", "gt_mpc") and solver.N == N
+    gt = mode == "gt_mpc"
+    E = len(specs)
+    B = 2 * E
+    rd = np.array([G.route_descriptor(r, exit_coord=G.EXIT_COORD.get(r)) for sp in specs for r in sp.routes], dtype=np.float64)
+    curv = np.array([G.curvature_params(r) for sp in specs for r in sp.routes], dtype=np.float64)
+    z = np.zeros((B, 7))
+    for e, sp in enumerate(specs):
+        for i in range(2):
+            x, y, th = G.frenet2global(sp.s0[i], sp.routes[i])
+            if sp.routes[i] in ('32', '41'):
+                th = abs(th)
+            z[2 * e + i] = (x, y, sp.s0[i], 0.0, 0.0, 0.0, th)
+    u_prev = np.tile([0.0, 0.0] if gt else [0.1, 0.0], (B, 1)).astype(np.float64)
+    enc = np.array([G.scenario_encoding(sp.routes) for sp in specs], dtype=np.float64).reshape(B)
+    z_cl = np.zeros((E, 2, steps + 1, 7)); u_cl = np.zeros((E, 2, steps, 2)); solved = np.zeros((E, 2, steps), dtype=np.int32)
+    ms = np.zeros(steps, dtype=np.float32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    rc = solver.lib.igt_episode_run_host(solver._h, E, steps, 1 if gt else 0, vp(rd), vp(curv), vp(z), vp(u_prev), vp(enc),
+                                         vp(z_cl), vp(u_cl), vp(solved), vp(ms) if record_latency else None)
+    solver._check(rc, "igt_episode_run_host")
+    solved = solved.astype(bool)
+    dist = np.sqrt(np.sum((z_cl[:, 0, :, :2] - z_cl[:, 1, :, :2]) ** 2, axis=-1))
+    final_s = z_cl[:, :, -1, 2]
+    return EpisodeResult(z_cl=z_cl, u_cl=u_cl, solved=solved, deadlock=np.sum(final_s <= 30, axis=1) >= 2,
+                         collision=dist.min(axis=1) < d_min - 1e-6, goal=final_s > 30,
+                         num_infeasible=(~solved).sum(axis=2), min_distance=dist.min(axis=1),
+                         step_latency_ms=[float(v) for v in ms] if record_latency else [])

@@ -136,6 +136,21 @@ def frenet2global(s, route, ey=0.0, W=ROAD_WIDTH, L=ROAD_LENGTH, ca=CA_RADIUS, e
     return x, y, th
 
 
+def route_descriptor(route, W=ROAD_WIDTH, L=ROAD_LENGTH, ca=CA_RADIUS, exit_coord=None):
+    """The 12 numbers the device-side closed loop needs to evaluate `frenet2global_xy` for this route
+    (csrc/episode.cuh route_xy): x0, y0, t0x, t0y, turn sign, b0, b1, r, exit axis (0: x, 1: y, -1: none), exit
+    coordinate, 0, 0."""
+    x0, y0, th0 = start_pose(route[0], W, L, ca)
+    t0 = (math.cos(th0), math.sin(th0))
+    sgn = turn_sign(route)
+    if sgn == 0:
+        return [x0, y0, t0[0], t0[1], 0.0, 1e30, 1e30, 1.0, -1.0, 0.0, 0.0, 0.0]
+    b0, b1, K = curvature_params(route, W, L, ca)
+    t1x = sgn * (-t0[1])
+    axis = -1.0 if exit_coord is None else (0.0 if abs(t1x) < 0.5 else 1.0)
+    return [x0, y0, t0[0], t0[1], float(sgn), b0, b1, 1.0 / abs(K), axis, 0.0 if exit_coord is None else float(exit_coord), 0.0, 0.0]
+
+
 def frenet2global_xy(s, route, W=ROAD_WIDTH, L=ROAD_LENGTH, ca=CA_RADIUS, exit_coord=None):
     """`frenet2global` (lane centre, ey = 0) for an array of arc lengths: s[...] -> x[...], y[...]."""
     s = np.asarray(s, dtype=np.float64)

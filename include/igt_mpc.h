@@ -158,6 +158,21 @@ int igt_solve_host(igt_handle *h, int B, const double *x0, const double *u_prev,
                    const double *obs_xy, const double *obs_psi, const double *nn_ctx, const double *u_init,
                    double *x, double *u, double *cost, double *viol, int *status, int *iters);
 
+/* Replaces the per-timestep loop of evaluate.py:451-564 ('mpc') / :198-312 ('gt_mpc') for E independent two-vehicle
+ * episodes: `steps` closed-loop steps entirely on the device -- per step one kernel for the glue before the solve
+ * (constant-acceleration forecast constant_acceleration_model.py:18-82, shared plans utils.py:339-352, filter_preds
+ * utils.py:365-388, warm start utils.py:354-363, value-network context mpc.py:326-337), one batched solve of all 2E
+ * vehicles (per-problem warm / cold start), one kernel after it (plant evaluate.py:491-510, brake fallback :511-545).
+ * Vehicle b = 2 e + i is agent i of episode e.  Host fp64 arrays:
+ *   route_desc[2E,12] = (x0, y0, t0x, t0y, turn sign, b0, b1, r, exit axis (0 x, 1 y, -1 none), exit coordinate, 0, 0):
+ *                       the closed-form lane centre of the vehicle's route (igt_mpc_int_b200/geometry.py);
+ *   curv[2E,3]; z0[2E,7] initial states; u_prev0[2E,2]; enc[2E] scenario codes (utils.py:141-169, gt_mpc only);
+ *   out: z_cl[E,2,steps+1,7], u_cl[E,2,steps,2], solved[E,2,steps] (int32), step_ms[steps] (device time per step; may
+ *   be NULL).  The handle's horizon N, limits and (gt_mpc != 0) value network apply; precision must be f64. */
+int igt_episode_run_host(igt_handle *h, int E, int steps, int gt_mpc, const double *route_desc, const double *curv,
+                         const double *z0, const double *u_prev0, const double *enc, double *z_cl, double *u_cl,
+                         int *solved, float *step_ms);
+
 /* Number of kernels this library has launched on `h` so far (bench.py's gpu_launches). */
 long long igt_launch_count(const igt_handle *h);
 

@@ -110,3 +110,53 @@ def test_closed_loop_gt_mpc_outcomes_match_oracle():
         if tc == 0:
             dz = np.abs(rg.z_cl - ro.z_cl).reshape(len(specs), -1).max(axis=1)
             assert np.mean(dz < 1e-3) >= 0.75, dz
+
+
+def test_route_descriptor_matches_closed_form():
+    """the 12-number route description the device loop uses reproduces geometry.frenet2global_xy (CPU restatement of
+    csrc/episode.cuh route_xy, same branches)"""
+    import math
+    s = np.linspace(0.0, 74.0, 371)
+    for r in G.ROUTES:
+        rd = G.route_descriptor(r, exit_coord=G.EXIT_COORD.get(r))
+        x0, y0, t0x, t0y, sgn, b0, b1, rr, axis, ec = rd[:10]
+        xs, ys = G.frenet2global_xy(s, r, exit_coord=G.EXIT_COORD.get(r))
+        for k, sk in enumerate(s):
+            if sgn == 0 or sk < b0:
+                x, y = x0 + sk * t0x, y0 + sk * t0y
+            else:
+                n0x, n0y = -t0y, t0x
+                cx, cy = x0 + b0 * t0x + sgn * rr * n0x, y0 + b0 * t0y + sgn * rr * n0y
+                if sk <= b1:
+                    phi = (sk - b0) / rr
+                    x = cx + rr * (math.sin(phi) * t0x - sgn * math.cos(phi) * n0x)
+                    y = cy + rr * (math.sin(phi) * t0y - sgn * math.cos(phi) * n0y)
+                else:
+                    x = cx + rr * t0x + (sk - b1) * sgn * n0x
+                    y = cy + rr * t0y + (sk - b1) * sgn * n0y
+                    if axis == 0:
+                        x = ec
+                    elif axis == 1:
+                        y = ec
+            assert abs(x - xs[k]) < 1e-12 and abs(y - ys[k]) < 1e-12, (r, sk)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["mpc", "gt_mpc"])
+def test_device_closed_loop_equals_host_driven_loop(mode):
+    """igt_episode_run_host (glue kernels on the device, per-problem warm flags, one call for all steps) against the
+    host-driven numpy loop with the same GPU solver: same outcomes on every episode, same trajectories up to the first
+    solve whose warm / cold batch composition lets round-off part two fp64 runs."""
+    from igt_mpc_int_b200.planner import BatchSolver
+    specs = episode.reference_episode_specs()[::4] if mode == "mpc" else episode.reference_episode_specs()[::8]
+    kw = dict(mlp=_value_net()) if mode == "gt_mpc" else {}
+    gpu = BatchSolver(N=40, **kw)
+    rh = episode.run_closed_loop(gpu, specs, steps=150, N=40, mode=mode)
+    rd = episode.run_closed_loop_device(gpu, specs, steps=150, N=40, mode=mode, record_latency=True)
+    gpu.close()
+    assert np.array_equal(rd.collision, rh.collision) and np.array_equal(rd.deadlock, rh.deadlock)
+    assert np.array_equal(rd.goal, rh.goal)
+    dz = np.abs(rd.z_cl - rh.z_cl).reshape(len(specs), -1).max(axis=1)
+    assert np.mean(dz < 1e-6) >= 0.85, dz
+    assert np.mean(rd.solved == rh.solved) > 0.995
+    assert len(rd.step_latency_ms) == 150 and min(rd.step_latency_ms) > 0
