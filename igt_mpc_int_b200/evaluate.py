@@ -54,7 +54,8 @@ def main(args, solver=None):
     for it in range(args.num_samples):
         all_specs = episode.reference_episode_specs(scenarios=[args.sc], sample=it, seed=seed)
         specs = [all_specs[r * 2 + o] for r, o in variants]
-        res = episode.run_closed_loop(solver, specs, steps=T, N=N, dt=dt, record_latency=True, mode=args.eval_mode)
+        loop = episode.run_closed_loop_device if getattr(args, 'device_loop', False) else episode.run_closed_loop
+        res = loop(solver, specs, steps=T, N=N, record_latency=True, mode=args.eval_mode)
         for e, sp in enumerate(specs):
             starts = [G.frenet2global(sp.s0[i], sp.routes[i]) for i in range(2)]
             refs = [RT.reference_dict(sp.routes[i], starts[i][0], starts[i][1], n=T) for i in range(2)]
@@ -86,6 +87,7 @@ def build_parser():
     p.add_argument('--all_variants', action='store_true')
     p.add_argument('--nn_weights', type=str, default=None)
     p.add_argument('--steps', type=int, default=150, help='closed-loop steps (the reference simulates 15 s = 150)')
+    p.add_argument('--device_loop', action='store_true', help='run the per-timestep glue on the GPU as well (igt_episode_run_host)')
     return p
 
 

@@ -48,3 +48,28 @@ def test_evaluate_writes_reference_files(tmp_path):
     rows = list(csv.DictReader(open(os.path.join(sub, 'eval_stats.csv'))))
     assert len(rows) == 2 and set(rows[0]) == {'avg_sol_times', 'std_solve_times', 'infeasible_ratio', 'deadlock'}
     assert len(summary) == 2 and summary[0]['routes'] == ['13', '23']
+
+
+import pytest
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_loop", [False, True])
+def test_evaluate_with_the_cuda_solver_writes_the_same_files(tmp_path, device_loop):
+    """BASELINE config 1 end to end on the GPU: `evaluate --eval_mode mpc --sc 1` with the CUDA solver (host-driven
+    loop and the on-device loop) writes the reference's result files, and they agree with the oracle-driven run."""
+    a = _args(tmp_path / "gpu", num_samples=1, steps=150, all_variants=True)
+    a.device_loop = device_loop
+    run_dir, summary = evaluate.main(a)
+    sub = os.path.join(run_dir, 'mpc')
+    cl = pickle.load(open(os.path.join(sub, 'cl_traj.pkl'), 'rb'))
+    data = pickle.load(open(os.path.join(sub, 'evaluation_data.pkl'), 'rb'))
+    rows = list(csv.DictReader(open(os.path.join(sub, 'eval_stats.csv'))))
+    assert cl.shape == (8, 14, 151) and data['x_cl'].shape == (8, 21, 151) and len(rows) == 8
+    ref_dir, ref_summary = evaluate.main(_args(tmp_path / "cpu", num_samples=1, steps=150, all_variants=True),
+                                         solver=OracleBackend(N=40, max_iter=60))
+    for g, o in zip(summary, ref_summary):
+        assert g['routes'] == o['routes'] and g['deadlock'] == o['deadlock'] and g['collision'] == o['collision'] and g['goal'] == o['goal']
+    cl_ref = pickle.load(open(os.path.join(ref_dir, 'mpc', 'cl_traj.pkl'), 'rb'))
+    close = np.abs(cl - cl_ref).reshape(8, -1).max(axis=1) < 1e-3
+    assert close.mean() >= 0.75
