@@ -934,6 +934,15 @@ int igt_debug_round_clocks(igt_handle *h, long long *clk512, int *n512)
     CK(cudaMemcpyFromSymbol(n512, g_round_n, 512 * sizeof(int)));
     return IGT_OK;
 }
+int igt_debug_round_max(igt_handle *h, int *mx512x4)
+{
+    if (!h || !mx512x4) return IGT_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(mx512x4, g_round_mx, 512 * 4 * sizeof(int)));
+    int z[512 * 4] = { 0 };
+    CK(cudaMemcpyToSymbol(g_round_mx, z, sizeof(z)));
+    return IGT_OK;
+}
 int igt_debug_round_phases(igt_handle *h, int *ph512x12)
 {
     if (!h || !ph512x12) return IGT_EINVAL;

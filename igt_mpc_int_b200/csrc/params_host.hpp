@@ -44,7 +44,7 @@ inline int default_params(igt_params *p, int precision)
     p->mu0 = 0.3; p->kappa_eps = 10.0; p->kappa_mu = 0.2; p->theta_mu = 1.5; p->y_init_min = 0.3;
     p->tau_min = 0.99; p->reg_min = 1e-4; p->reg_up = 10.0; p->reg_down = 10.0; p->reg_max = 1e10; p->reg_jump = 1.1;
     p->gamma_theta = 1e-6; p->max_iter = 60; p->n_alpha = 6; p->second_order = 1;
-    p->mu0_warm = 1e-4; p->y_init_min_warm = 1e-3;
+    p->mu0_warm = 1e-3; p->y_init_min_warm = 1e-2;   // see igt_mpc.h: softer than round 1's (1e-4, 1e-3)
     p->stall_iter = 16; p->stall_rp = 1e-2; p->max_trials = 0;
     p->precision = precision;
     p->acc_tol = 1e-3; p->acc_rp = 1e-6; p->acc_comp = 1e-4; p->x0_tol = 1e-6;

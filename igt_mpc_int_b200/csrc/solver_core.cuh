@@ -1845,6 +1845,7 @@ __device__ long long g_phase_clk[16];
 __device__ long long g_round_clk[512];   // per loop pass of CTA 0: cycles, and the number of its active problems
 __device__ int g_round_n[512];
 __device__ int g_round_ph[512][12];      // per loop pass: kcycles per phase
+__device__ int g_round_mx[512][4];       // per loop pass, max over CTA 0's threads: adjoint, Riccati (all retries), step bound kcycles; Riccati sweeps
 #define IGT_TICK(i) do { if (clk_on) { long long t_ = clock64(); clk[i] += t_ - clk_t; if (round_i < 512) g_round_ph[round_i][i] += (int)((t_ - clk_t) >> 10); clk_t = t_; } } while (0)
 #else
 #define IGT_TICK(i) do { } while (0)
@@ -1933,19 +1934,38 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         const bool back = active && sv.need_back;
         node_phase_cta<T, 1, STRIDE>(P, ws_base, sv.w.L, back && sv.need_back == 2, bound, sv, nl);
         IGT_TICK(1);
+#ifdef IGT_PHASE_CLOCKS
+        __shared__ int s_round_i;
+        if (clk_on) s_round_i = round_i;
+        __syncthreads();
+        const int rnd_ = s_round_i;
+        const long long ta_ = clock64();
+#endif
         const bool p2 = back && sv.backward_pre();              // adjoint sweep, convergence test, barrier update
+#ifdef IGT_PHASE_CLOCKS
+        if (blockIdx.x == 0 && back && rnd_ < 512) atomicMax(&g_round_mx[rnd_][0], (int)((clock64() - ta_) >> 10));
+#endif
         IGT_TICK(2);
         node_phase_cta<T, 2, STRIDE>(P, ws_base, sv.w.L, p2, bound, sv, nl);
         IGT_TICK(3);
         if (back && !sv.done) {                                  // Riccati sweep, step bound
 #ifdef IGT_PHASE_CLOCKS
+            const long long tr_ = clock64();
+            int nsw_ = 0;
             for (;;) {
+                nsw_++;
                 if (sv.riccati_sweep()) break;
                 sv.reg = fmax(fmax(sv.reg * P.reg_up, P.reg_min), sv.reg_hint);
                 if (sv.reg > P.reg_max) { sv.status = sv.acceptable() ? 6 : 3; sv.done = true; break; }
             }
+            const long long ts_ = clock64();
             IGT_TICK(4);
             if (!sv.done) { sv.need_back = 0; sv.ls = 0; sv.step_bound(); }
+            if (blockIdx.x == 0 && rnd_ < 512) {
+                atomicMax(&g_round_mx[rnd_][1], (int)((ts_ - tr_) >> 10));
+                atomicMax(&g_round_mx[rnd_][2], (int)((clock64() - ts_) >> 10));
+                atomicMax(&g_round_mx[rnd_][3], nsw_);
+            }
             IGT_TICK(5);
 #else
             sv.backward_post();

@@ -71,7 +71,11 @@ typedef struct {
     double tol_rp;     /* primal residual |c + slack|_inf (bounds the row violation) */
     double tol_comp;   /* complementarity max(mult*slack) */
     double mu0, mu_floor, kappa_eps, kappa_mu, theta_mu, y_init_min, tau_min;
-    double mu0_warm, y_init_min_warm;   /* used instead of mu0 / y_init_min when u_init is given */
+    double mu0_warm, y_init_min_warm;   /* used instead of mu0 / y_init_min when u_init is given.  Defaults 1e-3 / 1e-2: the
+                                           reference restarts IPOPT from the shifted primal plan only (mpc.py:386-389; IPOPT's
+                                           mu_init stays 0.1), and a hard warm start (1e-4 / 1e-3) cannot move a shifted plan
+                                           that sits on its rows: over the 64 reference episodes it fails 7.5 % of the solves
+                                           and deadlocks 13 episodes, the softer one 4.7 % and 6, for 3 more iterations */
     double reg_min, reg_up, reg_down, reg_max;
     double reg_jump;   /* after a Riccati stage whose Quu + reg I is not positive definite: reg >= reg_jump * (-lambda_min(Quu))
                           of that stage (besides reg * reg_up), so the inertia correction takes 1-2 retries, not 6 */

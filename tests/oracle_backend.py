@@ -12,7 +12,7 @@ class OracleBackend:
         self.options = options
         term = None if mlp is None else nlp.MLPTerm(**mlp)
         self.cold = c_oracle.COracle(self.P, term, **options)
-        warm = dict(options); warm.update(mu0=1e-4, y_init_min=1e-3)      # igt_params mu0_warm / y_init_min_warm
+        warm = dict(options); warm.update(mu0=1e-3, y_init_min=1e-2)      # igt_params mu0_warm / y_init_min_warm
         self.warm = c_oracle.COracle(self.P, term, **warm)
         self.plain = c_oracle.COracle(self.P, **options)                  # 'mpc' cost: evaluate() without a value-network context
 

@@ -20,6 +20,10 @@ if GT:
 else:
     s = BatchSolver(N=N)
 out = s.solve_batch_device(x0, up, cv, ob, **kw); torch.cuda.synchronize()
+lib0 = _lib.load()
+if hasattr(lib0, "igt_debug_round_max"):
+    lib0.igt_debug_round_max.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib0.igt_debug_round_max(s._h, (C.c_int * 2048)())          # reset after the warm-up solve
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); out = s.solve_batch_device(x0, up, cv, ob, out=out, **kw); e1.record(); torch.cuda.synchronize()
 clk = (C.c_longlong * 16)()
@@ -47,3 +51,11 @@ if hasattr(lib, "igt_debug_round_phases"):
     for i in range(512):
         if rn[i] > 0 and (i < 30 or i % 4 == 0):
             print("%3d n=%3d | " % (i, rn[i]) + " ".join("%7d" % ph[i * 12 + j] for j in range(12)))
+
+if hasattr(lib, "igt_debug_round_max"):
+    mx = (C.c_int * 2048)()
+    assert lib.igt_debug_round_max(s._h, mx) == 0
+    print("per pass, max over CTA 0's threads (kcycles): adjoint+test | riccati (all sweeps) | step bound | riccati sweeps")
+    for i in range(512):
+        if rn[i] > 0 and (i < 30 or i % 2 == 0):
+            print("%3d n=%3d | %6d %6d %6d  x%d" % (i, rn[i], mx[4 * i], mx[4 * i + 1], mx[4 * i + 2], mx[4 * i + 3]))
