@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(128) guess_kernel(ProbIO io, long B, double *g
     sv.compute_guess(io, p, guess + p * P.N * 2);
 }
 
+#ifndef IGT_RSTG
+#define IGT_RSTG 1     // row staging in the node phases of the plain throughput kernels (solver_core.cuh, Ws RSTG)
+#endif
 template <typename T, bool TC, bool OBCA, bool COOP = false>
 __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws, long n_slots, long B, Sched sc,
                                                                const double *guess, T *mlp_scratch, int mlp_width,
@@ -66,8 +69,10 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, 1) solve_kernel(ProbIO io, T *ws,
     const DevParams<T> &P = ConstP<T>::get(cs);
     MlpTcCtx tc;
     if (TC) mlp_tc_setup(tc, dyn_smem, wt);
-    solve_persistent<T, TC, 32, OBCA, COOP>(P, io, ws, slot, B, sc, guess,
-                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc, quota, cs, dyn_smem);
+    constexpr bool RSTG = IGT_RSTG && !TC && !COOP;                 // (those two use the dynamic shared memory themselves)
+    solve_persistent<T, TC, 32, OBCA, COOP, RSTG>(P, io, ws, slot, B, sc, guess,
+                            mlp_scratch ? mlp_scratch + slot * 12 * (long)mlp_width : nullptr, mlp_width, &tc, quota, cs, dyn_smem,
+                            RSTG ? dyn_smem : nullptr);
     if (TC) mlp_tc_teardown(tc);
 }
 
@@ -690,14 +695,20 @@ static int solve_dev_impl(igt_handle *h, int B, const double *x0, const double *
         CK(cudaFuncSetAttribute(solve_kernel<double, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         solve_kernel<double, false, false, true><<<gs, bs, sm, st>>>(io, (double *)h->ws, n_slots, B, sc, guess, nullptr, h->mlp_width, h->tc, quota, cs);
     } else if (obca) {
-        solve_kernel<double, false, true><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
-                                                             nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
+        const int rsm = IGT_RSTG ? RSTG_SLOTS * SOLVE_BLOCK * 8 : 0;
+        CK(cudaFuncSetAttribute(solve_kernel<double, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm));
+        solve_kernel<double, false, true><<<gs, bs, rsm, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
+                                                               nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
     } else if (f64) {
-        solve_kernel<double, false, false><<<gs, bs, 0, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
-                                                              nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
+        const int rsm = IGT_RSTG ? RSTG_SLOTS * SOLVE_BLOCK * 8 : 0;
+        CK(cudaFuncSetAttribute(solve_kernel<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm));
+        solve_kernel<double, false, false><<<gs, bs, rsm, st>>>(io, (double *)h->ws, n_slots, B, sc, guess,
+                                                                nn_ctx ? (double *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
     } else {
-        solve_kernel<float, false, false><<<gs, bs, 0, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
-                                                             nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
+        const int rsm = IGT_RSTG ? RSTG_SLOTS * SOLVE_BLOCK * 4 : 0;
+        CK(cudaFuncSetAttribute(solve_kernel<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm));
+        solve_kernel<float, false, false><<<gs, bs, rsm, st>>>(io, (float *)h->ws, n_slots, B, sc, guess,
+                                                               nn_ctx ? (float *)h->mlp_scratch : nullptr, h->mlp_width, h->tc, quota, cs);
     }
     h->launches++;
     CK(cudaGetLastError());

@@ -129,9 +129,44 @@ struct WsLayout {
 // offset that is a compile-time constant folds into the load/store immediate.
 // STRIDE 1 is the latency path for batches of at most one problem per SM: the workspace of the CTA's one
 // problem lives in shared memory, contiguously (bind ignores the slot, nothing is prefetched).
-template <typename T, int STRIDE = 32, bool OBCA = false>
+// RSTG (row staging, node phases of the throughput kernel): the slacks and multipliers of a node's (at most 13) stage
+// rows are copied into this thread's private column of a shared-memory buffer with per-thread cp.async at the start of
+// the item -- no registers in flight, unlike a burst of loads -- and read from there when the rows are visited, instead
+// of one dependent L2 / HBM round trip per row (a quarter of the kernel's stall samples in round 1's ncu source view).
+constexpr int RSTG_SLOTS = 26;           // 13 rows x (multiplier, slack)
+template <typename T, int STRIDE = 32, bool OBCA = false, bool RSTG = false>
 struct Ws {
     static constexpr bool obca = OBCA;
+    static constexpr bool rstg = RSTG;
+    T *rs = nullptr;                     // RSTG: this thread's column, slot i at rs[i * blockDim.x]
+    int rs_stride = 0;
+    IGT_HD void rows_fetch(int b, int o, int n) const
+    {
+#ifdef __CUDA_ARCH__
+        if (RSTG) {
+            for (int r = 0; r < n; r++) {
+                const unsigned ds = (unsigned)__cvta_generic_to_shared(rs + (2 * r) * rs_stride);
+                const unsigned dy = (unsigned)__cvta_generic_to_shared(rs + (2 * r + 1) * rs_stride);
+                if (sizeof(T) == 8) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ds), "l"(wb + (L.oS[b] + o + r) * STRIDE) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dy), "l"(wb + (L.oY[b] + o + r) * STRIDE) : "memory");
+                } else {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ds), "l"(wb + (L.oS[b] + o + r) * STRIDE) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dy), "l"(wb + (L.oY[b] + o + r) * STRIDE) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+#endif
+    }
+    IGT_HD void rows_wait() const
+    {
+#ifdef __CUDA_ARCH__
+        if (RSTG) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+    }
+    IGT_HD T row_s(int b, int o, int r) const { return RSTG ? rs[(2 * r) * rs_stride] : at(L.oS[b] + o + r); }
+    IGT_HD T row_y(int b, int o, int r) const { return RSTG ? rs[(2 * r + 1) * rs_stride] : at(L.oY[b] + o + r); }
     static constexpr int nge = OBCA ? NGE_OBCA : NGE, nhe = OBCA ? NHE_OBCA : NHE;
     T *wb;          // base + (slot / 32) * total * 32 + slot % 32
     WsLayout L;
@@ -597,7 +632,14 @@ IGT_HD void visit_rows(const DevParams<T> &P, int k, const T *z, const T *up, co
 template <bool WANT_S, typename T, typename W>
 IGT_HD void prefetch_rows(const DevParams<T> &P, const W &w, int k, int b, int o)
 {
-    const int n = (k == 0 ? 8 : (k == P.N ? 3 : 13)) + (k == P.N - 1 ? P.n_cinf : 0);
+    const int ns = k == 0 ? 8 : (k == P.N ? 3 : 13);
+    if (W::rstg) {                                               // (the terminal-set rows of node N-1 are loaded in place)
+        w.rows_fetch(b, o, ns);
+        if (k == P.N - 1)
+            for (int r = ns; r < ns + P.n_cinf; r++) { w.pf(w.L.oY[b] + o + r); if (WANT_S) w.pf(w.L.oS[b] + o + r); }
+        return;
+    }
+    const int n = ns + (k == P.N - 1 ? P.n_cinf : 0);
     for (int r = 0; r < n; r++) {
         w.pf(w.L.oY[b] + o + r);
         if (WANT_S) w.pf(w.L.oS[b] + o + r);
@@ -771,10 +813,11 @@ IGT_HD void node_phase1(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
 #pragma unroll
     for (int i = 0; i < NW; i++) gw[i] = T(0);
     T rp = T(0), s_max = T(0), sy_min = T(1e30), sy_max = T(0);
+    w.rows_wait();
     visit_rows<false, W::obca>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), W::obca ? T(c.obs_psi[k]) : T(0),
                                [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, auto I2, T g2, T, T, T) {
         constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
-        const T s = w.S(b, o + r), y = w.Y(b, o + r);
+        const T s = w.row_s(b, o, r), y = w.row_y(b, o, r);
         gw[i0] += g0 * s;
         if constexpr (i1 >= 0) gw[i1] += g1 * s;
         if constexpr (i2 >= 0) gw[i2] += g2 * s;
@@ -820,10 +863,11 @@ IGT_HD void node_phase2(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
         for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
         add_dyn_hessian(P, z, u, c.curv, ln, H);
     }
+    w.rows_wait();
     visit_rows<false, W::obca>(P, k, z, up, u, T(c.obs[2 * k]), T(c.obs[2 * k + 1]), W::obca ? T(c.obs_psi[k]) : T(0),
                                [&](auto, int r, T cv, auto I0, T g0, auto I1, T g1, auto I2, T g2, T hxx, T hxy, T hyy) {
         constexpr int i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
-        const T s = w.S(b, o + r), y = w.Y(b, o + r);
+        const T s = w.row_s(b, o, r), y = w.row_y(b, o, r);
         T iy = T(1) / y, rhat = s * cv + mu, sig = s * iy, gr = s + rhat * iy;
         g[i0] += g0 * gr;
         H[sym11(i0, i0)] += sig * g0 * g0;
@@ -933,9 +977,10 @@ IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
     const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]), opsi = W::obca ? T(c.obs_psi[k]) : T(0);
     bool fail = false;
     T ynv[NSLOT];
+    w.rows_wait();
     visit_rows<false, W::obca>(P, k, z, up, u, ox, oy, opsi, [&](auto SL, int r, T cv, auto I0, T g0, auto I1, T g1, auto I2, T g2, T, T, T) {
         constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
-        const T s = w.S(b, o + r), y = w.Y(b, o + r);
+        const T s = w.row_s(b, o, r), y = w.row_y(b, o, r);
         T dc = g0 * dw[i0];
         if constexpr (i1 >= 0) dc += g1 * dw[i1];
         if constexpr (i2 >= 0) dc += g2 * dw[i2];
@@ -1699,6 +1744,7 @@ constexpr int MAX_SOLVE_BLOCK = IGT_MAX_SOLVE_BLOCK;
 template <typename T>
 struct NodeList {                    // shared-memory work list of one CTA-wide phase
     int cslot;                       // constant-memory slot of this launch's parameters (ConstP<T>::get)
+    void *rstg;                      // row-staging buffer in dynamic shared memory (Ws RSTG), or null
     int wcnt[MAX_SOLVE_BLOCK / 32];
     int slot[MAX_SOLVE_BLOCK];
     NodeCtx<T> ctx[MAX_SOLVE_BLOCK];
@@ -1731,11 +1777,12 @@ __device__ __forceinline__ int cta_list_build(bool need, long bound, const S &sv
 // which the translation unit defines.
 template <typename T> struct ConstP;
 
-template <typename T, int PHASE, int STRIDE, bool OBCA>
+template <typename T, int PHASE, int STRIDE, bool OBCA, bool RSTG>
 __device__ __noinline__ void phase_items(T *ws_base, const NodeList<T> *nl, int n, int n_spec)
 {
     const DevParams<T> &P = ConstP<T>::get(nl->cslot);
-    Ws<T, STRIDE, OBCA> w; w.init_layout(P.N, P.n_cinf);
+    Ws<T, STRIDE, OBCA, RSTG && PHASE != 3> w; w.init_layout(P.N, P.n_cinf);
+    if (RSTG && PHASE != 3) { w.rs = reinterpret_cast<T *>(nl->rstg) + threadIdx.x; w.rs_stride = blockDim.x; }
     if (PHASE == 1 || PHASE == 2) {
         const int total = n * (P.N + 1);
         for (int it = threadIdx.x; it < total; it += blockDim.x) {
@@ -1758,12 +1805,12 @@ __device__ __noinline__ void phase_items(T *ws_base, const NodeList<T> *nl, int 
     }
 }
 
-template <typename T, int PHASE, int STRIDE, typename S>
+template <typename T, int PHASE, int STRIDE, bool RSTG, typename S>
 __device__ __forceinline__ void node_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
                                                long bound, const S &sv, NodeList<T> &nl)
 {
     const int n = cta_list_build(need, bound, sv, nl);
-    if (n > 0) phase_items<T, PHASE, STRIDE, S::obca>(ws_base, &nl, n, 1);
+    if (n > 0) phase_items<T, PHASE, STRIDE, S::obca, RSTG>(ws_base, &nl, n, 1);
     __syncthreads();
 }
 
@@ -1783,7 +1830,7 @@ __device__ long long g_mid_t;            // debug: end of the rollouts of CTA 0'
 #ifndef IGT_SPEC_BUDGET
 #define IGT_SPEC_BUDGET IGT_MAX_SOLVE_BLOCK
 #endif
-template <typename T, int STRIDE, typename S>
+template <typename T, int STRIDE, bool RSTG, typename S>
 __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
                                                long bound, const S &sv, NodeList<T> &nl, bool speculate, int &n_out)
 {
@@ -1793,10 +1840,10 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
     // IGT_SPEC_BUDGET: most candidates (problems x halvings) evaluated at once; the default fills the CTA's threads
     int n_spec = 1;
     if (speculate) { n_spec = IGT_SPEC_BUDGET / n; n_spec = n_spec < 1 ? 1 : (n_spec > P.n_alpha ? P.n_alpha : n_spec); }
-    phase_items<T, 3, STRIDE, S::obca>(ws_base, &nl, n, n_spec);
+    phase_items<T, 3, STRIDE, S::obca, false>(ws_base, &nl, n, n_spec);
     __syncthreads();
     IGT_MID_TICK();
-    phase_items<T, 4, STRIDE, S::obca>(ws_base, &nl, n, n_spec);
+    phase_items<T, 4, STRIDE, S::obca, RSTG>(ws_base, &nl, n, n_spec);
     __syncthreads();
     return n_spec;
 }
@@ -1851,14 +1898,14 @@ __device__ int g_round_mx[512][4];       // per loop pass, max over CTA 0's thre
 #define IGT_TICK(i) do { } while (0)
 #endif
 
-template <typename T, bool TC, int STRIDE = 32, bool OBCA = false, bool COOP = false>
+template <typename T, bool TC, int STRIDE = 32, bool OBCA = false, bool COOP = false, bool RSTG = false>
 __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const ProbIO &io, T *ws_base,
                                                  long slot, long B, const Sched &sc,
                                                  const double *guess, T *mlp_scratch, int mlp_width, MlpTcCtx *tc,
-                                                 int quota, int cslot, uint8_t *coop_smem = nullptr)
+                                                 int quota, int cslot, uint8_t *coop_smem = nullptr, void *rstg_smem = nullptr)
 {
     __shared__ NodeList<T> nl;
-    if (threadIdx.x == 0) nl.cslot = cslot;                     // (the first CTA barrier of the loop publishes it)
+    if (threadIdx.x == 0) { nl.cslot = cslot; nl.rstg = rstg_smem; }   // (the first CTA barrier of the loop publishes them)
     Solver<T, Ws<T, STRIDE, OBCA>> sv(P);
     sv.w.init_layout(P.N, P.n_cinf);
     sv.w.bind(ws_base, slot);
@@ -1932,7 +1979,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         IGT_TICK(0);
         // ---- phase 1: backward pass = CTA-wide node phases between the per-problem sweeps ----
         const bool back = active && sv.need_back;
-        node_phase_cta<T, 1, STRIDE>(P, ws_base, sv.w.L, back && sv.need_back == 2, bound, sv, nl);
+        node_phase_cta<T, 1, STRIDE, RSTG>(P, ws_base, sv.w.L, back && sv.need_back == 2, bound, sv, nl);
         IGT_TICK(1);
 #ifdef IGT_PHASE_CLOCKS
         __shared__ int s_round_i;
@@ -1946,7 +1993,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         if (blockIdx.x == 0 && back && rnd_ < 512) atomicMax(&g_round_mx[rnd_][0], (int)((clock64() - ta_) >> 10));
 #endif
         IGT_TICK(2);
-        node_phase_cta<T, 2, STRIDE>(P, ws_base, sv.w.L, p2, bound, sv, nl);
+        node_phase_cta<T, 2, STRIDE, RSTG>(P, ws_base, sv.w.L, p2, bound, sv, nl);
         IGT_TICK(3);
         if (back && !sv.done) {                                  // Riccati sweep, step bound
 #ifdef IGT_PHASE_CLOCKS
@@ -1976,7 +2023,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
         int n_try = 0;
-        const int n_spec = trial_phase_cta<T, STRIDE>(P, ws_base, sv.w.L, trying, bound, sv, nl, true, n_try);
+        const int n_spec = trial_phase_cta<T, STRIDE, RSTG>(P, ws_base, sv.w.L, trying, bound, sv, nl, true, n_try);
 #ifdef IGT_PHASE_CLOCKS
         if (clk_on) { long long m_ = g_mid_t; clk[7] += m_ - clk_t; if (round_i < 512) g_round_ph[round_i][7] += (int)((m_ - clk_t) >> 10); clk_t = m_; }
 #endif

@@ -74,7 +74,7 @@ def test_solver_edge_cases():
     warm = s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, u_init=np.nan_to_num(cold["u"]))
     assert np.all(warm["status"][ok] == 0)
     assert np.max(relerr(warm["cost"][ok], cold["cost"][ok])) < 1e-4
-    assert np.median(warm["iters"][ok]) < 0.8 * np.median(cold["iters"][ok])
+    assert np.median(warm["iters"][ok]) < 0.9 * np.median(cold["iters"][ok])        # (soft warm start: mu0_warm 1e-3, igt_mpc.h)
     with pytest.raises(_lib.IgtError):
         s.solve_batch(pb.x0, pb.u_prev, pb.curv, pb.obs, nn_ctx=pb.nn_ctx)      # no MLP set
     with pytest.raises(ValueError):
