@@ -121,19 +121,25 @@ __global__ void __launch_bounds__(128) rollout_kernel(int B, const float *__rest
                 Bk[i * 2] = S[i][4]; Bk[i * 2 + 1] = S[i][5];
             }
         }
-        // compensated value step: the same stage derivatives as rk4_core, Kahan-summed increments
+        // compensated value step: the same stage derivatives as rk4_core, Kahan-summed increments.  The pw_const branch
+        // of every evaluation (mpc.py:199: K steps at s = b0, b1) is decided in DOUBLE from the compensated arc length
+        // (z - comp is the running sum to about fp64 accuracy): in plain fp32 a stage state within 5e-5 m of a break-point
+        // takes the other branch than the fp64 reference (0.1 % of rollouts missed the 1e-5 target in round 1).
         const StepK<float> c = step_setup(P, z, u, curv);
+        const double b0d = curv[0], b1d = curv[1];
+        auto Kof = [&](double sd) { return (sd >= b0d ? curv[2] : 0.f) - (sd >= b1d ? curv[2] : 0.f); };
         for (int it = 0; it < P.n_rk; it++) {
             Deriv<float> k1, k2, k3, k4;
             RhsJac<float> J;
             const float hh = 0.5f * h;
-            stage_deriv<float, false>(c, z[IS], z[IEY], z[IEPSI], z[IV], z[IPSI], k1, J);
-            stage_deriv<float, false>(c, z[IS] + hh * k1.s, z[IEY] + hh * k1.ey, z[IEPSI] + hh * k1.ep, z[IV] + hh * u[0],
-                                      z[IPSI] + hh * k1.ps, k2, J);
-            stage_deriv<float, false>(c, z[IS] + hh * k2.s, z[IEY] + hh * k2.ey, z[IEPSI] + hh * k2.ep, z[IV] + hh * u[0],
-                                      z[IPSI] + hh * k2.ps, k3, J);
-            stage_deriv<float, false>(c, z[IS] + h * k3.s, z[IEY] + h * k3.ey, z[IEPSI] + h * k3.ep, z[IV] + h * u[0],
-                                      z[IPSI] + hh * k3.ps, k4, J);      // psi + h/2 k3: the reference's k4 quirk
+            const double sd = (double)z[IS] - (double)comp[IS];
+            stage_deriv<float, false, true>(c, z[IS], z[IEY], z[IEPSI], z[IV], z[IPSI], k1, J, Kof(sd));
+            stage_deriv<float, false, true>(c, z[IS] + hh * k1.s, z[IEY] + hh * k1.ey, z[IEPSI] + hh * k1.ep, z[IV] + hh * u[0],
+                                            z[IPSI] + hh * k1.ps, k2, J, Kof(sd + (double)hh * (double)k1.s));
+            stage_deriv<float, false, true>(c, z[IS] + hh * k2.s, z[IEY] + hh * k2.ey, z[IEPSI] + hh * k2.ep, z[IV] + hh * u[0],
+                                            z[IPSI] + hh * k2.ps, k3, J, Kof(sd + (double)hh * (double)k2.s));
+            stage_deriv<float, false, true>(c, z[IS] + h * k3.s, z[IEY] + h * k3.ey, z[IEPSI] + h * k3.ep, z[IV] + h * u[0],
+                                            z[IPSI] + hh * k3.ps, k4, J, Kof(sd + (double)h * (double)k3.s));      // psi + h/2 k3: the reference's k4 quirk
             float inc[NZ];
             inc[IX] = h / 6.f * (k1.x + 2.f * k2.x + 2.f * k3.x + k4.x);
             inc[IY] = h / 6.f * (k1.y + 2.f * k2.y + 2.f * k3.y + k4.y);

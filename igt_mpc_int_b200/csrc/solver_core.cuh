@@ -304,8 +304,10 @@ struct Deriv { T s, ey, ep, x, y, ps; };
 template <typename T>
 struct RhsJac { T s_ey, s_ep, s_v, s_d, ey_ep, ey_v, ey_d, e_ey, e_ep, e_v, e_d, x_v, x_ps, x_d, y_v, y_ps, y_d, p_v, p_d; };
 
-template <typename T, bool JAC>
-IGT_HD void stage_deriv(const StepK<T> &c, T s, T ey, T ep, T v, T ps, Deriv<T> &d, RhsJac<T> &J)
+// KF: the curvature of this evaluation is given (Kf) instead of looked up from s -- the fp32 rollout kernel decides the
+// pw_const branch in double from its compensated arc length, see rollout_kernel
+template <typename T, bool JAC, bool KF = false>
+IGT_HD void stage_deriv(const StepK<T> &c, T s, T ey, T ep, T v, T ps, Deriv<T> &d, RhsJac<T> &J, T Kf = T(0))
 {   // kinematic_bicycle_model_frenet.py:71-91
     T s1, c1, sp, cp;
     {
@@ -316,7 +318,7 @@ IGT_HD void stage_deriv(const StepK<T> &c, T s, T ey, T ep, T v, T ps, Deriv<T> 
     }
     T K = T(0), iden = T(1);
     if (c.kv != T(0)) {                                        // straight routes: no curvature test, no division
-        K = curvature(s, c.b0, c.b1, c.kv);
+        K = KF ? Kf : curvature(s, c.b0, c.b1, c.kv);
         if (K != T(0)) iden = T(1) / (T(1) - K * ey);
     }
     const T sdot = v * c1 * iden;

@@ -38,9 +38,10 @@ def test_frenet_rollout_large_batch_vs_oracle(solver, oracle_params):
     Zo, Ao, Bo = c_oracle.COracle(oracle_params[N]).rollout(z0, U, cv, jac=True)
     Z, A, Bm = solver.rollout(z0, U, cv, jac=True)
     e = relerr(Z, Zo).reshape(B, -1).max(1)
-    # a sample whose s lands within fp32 round-off of a curvature breakpoint may take the other
-    # pw_const branch; everything else must meet 1e-5
-    assert np.mean(e < 1e-5) > 0.999, "fraction below 1e-5: %g, max %g" % (np.mean(e < 1e-5), e.max())
+    # every rollout meets 1e-5: the kernel decides the pw_const branch in double from its compensated arc length, so a
+    # stage state next to a curvature break-point takes the fp64 reference's branch (round 1: 0.1 % did not)
+    print("fraction below 1e-5: %.6f, max %g" % (np.mean(e < 1e-5), e.max()))
+    assert np.max(e) < 1e-5, "fraction below 1e-5: %g, max %g" % (np.mean(e < 1e-5), e.max())
     good = e < 1e-5
     # Jacobians: 1e-4 relative (metric |d| / max(|ref|, 1))
     assert np.max(relerr(A[good], Ao[good])) < 1e-4 and np.max(relerr(Bm[good], Bo[good])) < 1e-4
