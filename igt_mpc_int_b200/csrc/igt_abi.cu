@@ -962,6 +962,14 @@ int igt_debug_round_max(igt_handle *h, int *mx512x4)
     CK(cudaMemcpyToSymbol(g_round_mx, z, sizeof(z)));
     return IGT_OK;
 }
+int igt_debug_cta_clocks(igt_handle *h, long long *clk512, int *rounds512)
+{
+    if (!h || !clk512 || !rounds512) return IGT_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(clk512, g_cta_clk, 512 * sizeof(long long)));
+    CK(cudaMemcpyFromSymbol(rounds512, g_cta_rounds, 512 * sizeof(int)));
+    return IGT_OK;
+}
 int igt_debug_round_phases(igt_handle *h, int *ph512x12)
 {
     if (!h || !ph512x12) return IGT_EINVAL;

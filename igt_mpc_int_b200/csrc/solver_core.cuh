@@ -1620,10 +1620,11 @@ struct Solver {
     // judge candidates 0 .. nj-1 in the order sequential halving would try them
     // (stored: the terminal value terms of the candidates were evaluated CTA-wide on the tensor cores and
     // left in Tc(buffer, 2..7), see tc_candidates)
-    IGT_HD void accept_trials(int nj, bool stored = false)
+    // judge candidates j0 .. j1-1 (none of the earlier ones passed); returns the first that passes or -1
+    IGT_HD int judge_trials(int j0, int j1, bool stored, int &tried)
     {
-        int jacc = -1, tried = 0;
-        for (int j = 0; j < nj && jacc < 0; j++) {
+        int jacc = -1;
+        for (int j = j0; j < j1 && jacc < 0; j++) {
             trials++; tried++;
             collect_trial(j);
             if (trial_ok) {
@@ -1637,6 +1638,12 @@ struct Solver {
             }
             if (trial_passes()) jacc = j;
         }
+        return jacc;
+    }
+    IGT_HD void accept_trials(int nj, bool stored = false)
+    {
+        int tried = 0;
+        const int jacc = judge_trials(0, nj, stored, tried);
         finish_trials(jacc, tried);
     }
 
@@ -1749,13 +1756,14 @@ struct NodeList {                    // shared-memory work list of one CTA-wide 
     void *rstg;                      // row-staging buffer in dynamic shared memory (Ws RSTG), or null
     int wcnt[MAX_SOLVE_BLOCK / 32];
     int slot[MAX_SOLVE_BLOCK];
+    int more[MAX_SOLVE_BLOCK];       // CTA-wide value term, second pass: this problem's first candidate was rejected
     NodeCtx<T> ctx[MAX_SOLVE_BLOCK];
 };
 
 // compact the problems of the CTA that need a phase into the shared work list (slot order is kept,
 // so that neighbouring lanes mostly work on neighbouring slots); returns their number
 template <typename T, typename S>
-__device__ __forceinline__ int cta_list_build(bool need, long bound, const S &sv, NodeList<T> &nl)
+__device__ __forceinline__ int cta_list_build(bool need, long bound, const S &sv, NodeList<T> &nl, int *my_idx = nullptr)
 {
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -1768,6 +1776,7 @@ __device__ __forceinline__ int cta_list_build(bool need, long bound, const S &sv
         const int idx = base + __popc(m & ((1u << lane) - 1u));
         nl.slot[idx] = (int)bound;
         nl.ctx[idx] = sv.node_ctx();
+        if (my_idx) *my_idx = idx;
     }
     __syncthreads();
     return n;
@@ -1834,9 +1843,10 @@ __device__ long long g_mid_t;            // debug: end of the rollouts of CTA 0'
 #endif
 template <typename T, int STRIDE, bool RSTG, typename S>
 __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base, const WsLayout &L, bool need,
-                                               long bound, const S &sv, NodeList<T> &nl, bool speculate, int &n_out)
+                                               long bound, const S &sv, NodeList<T> &nl, bool speculate, int &n_out,
+                                               int *my_idx = nullptr)
 {
-    const int n = cta_list_build(need, bound, sv, nl);
+    const int n = cta_list_build(need, bound, sv, nl, my_idx);
     n_out = n;
     if (n == 0) { IGT_MID_TICK(); return 1; }                     // CTA-uniform
     // IGT_SPEC_BUDGET: most candidates (problems x halvings) evaluated at once; the default fills the CTA's threads
@@ -1856,11 +1866,12 @@ __device__ __forceinline__ int trial_phase_cta(const DevParams<T> &P, T *ws_base
 // COOP: the same with the exact cooperative evaluation (mlp_coop.cuh) instead of the tensor cores.
 template <typename T, bool COOP, typename WS>
 __device__ __forceinline__ void tc_candidates(const DevParams<T> &P, const ProbIO &io, T *ws_base, const WS &wproto,
-                                              const NodeList<T> &nl, int n, int n_spec, MlpTcCtx *tc, uint8_t *coop_smem)
+                                              const NodeList<T> &nl, int n, int n_spec, MlpTcCtx *tc, uint8_t *coop_smem,
+                                              int jlo = 0, bool filter = false)
 {
     if (n == 0) return;                                            // CTA-uniform
-    const int t = threadIdx.x, q = t % n, j = t / n;
-    bool valid = t < n * n_spec && j < P.n_alpha - nl.ctx[q].ls;
+    const int t = threadIdx.x, q = t % n, j = jlo + t / n;
+    bool valid = j < n_spec && j < P.n_alpha - nl.ctx[q].ls && (!filter || nl.more[q]);
     WS w = wproto;
     int nb = 0;
     using V = typename std::conditional<COOP, T, float>::type;
@@ -1894,6 +1905,8 @@ __device__ long long g_phase_clk[16];
 __device__ long long g_round_clk[512];   // per loop pass of CTA 0: cycles, and the number of its active problems
 __device__ int g_round_n[512];
 __device__ int g_round_ph[512][12];      // per loop pass: kcycles per phase
+__device__ long long g_cta_clk[512];     // per CTA: cycles from its start to its exit, and its loop passes
+__device__ int g_cta_rounds[512];
 __device__ int g_round_mx[512][4];       // per loop pass, max over CTA 0's threads: adjoint, Riccati (all retries), step bound kcycles; Riccati sweeps
 #define IGT_TICK(i) do { if (clk_on) { long long t_ = clock64(); clk[i] += t_ - clk_t; if (round_i < 512) g_round_ph[round_i][i] += (int)((t_ - clk_t) >> 10); clk_t = t_; } } while (0)
 #else
@@ -1923,7 +1936,8 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
 #ifdef IGT_PHASE_CLOCKS
     const bool clk_on = blockIdx.x == 0 && threadIdx.x == 0;
     long long clk[16] = { 0 }, clk_t = clock64(), round_t = clk_t;
-    int round_i = 0;
+    const long long cta_t0 = clk_t;
+    int round_i = 0, cta_rounds = 0;
     if (clk_on) for (int i = 0; i < 12; i++) g_round_ph[0][i] = 0;
 #endif
     // All warps of the CTA (one CTA per SM) walk the phases together -- scheduling, backward
@@ -1967,6 +1981,7 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         // a warp is finished once its lanes can fetch no more and none of them is busy
         const bool wants_exit = __all_sync(FULL, exhausted && !active);
 #ifdef IGT_PHASE_CLOCKS
+        cta_rounds++;
         const int cta_busy = __syncthreads_count(active);
         if (clk_on && round_i < 512) {
             long long t_ = clock64();
@@ -2025,21 +2040,38 @@ __device__ __forceinline__ void solve_persistent(const DevParams<T> &P, const Pr
         // ---- phase 2: one forward trial + acceptance ----
         const bool trying = active && !sv.done;
         int n_try = 0;
-        const int n_spec = trial_phase_cta<T, STRIDE, RSTG>(P, ws_base, sv.w.L, trying, bound, sv, nl, true, n_try);
+        int my_idx = 0;                                          // this owner's position in the trial phase's list
+        const int n_spec = trial_phase_cta<T, STRIDE, RSTG>(P, ws_base, sv.w.L, trying, bound, sv, nl, true, n_try, &my_idx);
 #ifdef IGT_PHASE_CLOCKS
         if (clk_on) { long long m_ = g_mid_t; clk[7] += m_ - clk_t; if (round_i < 512) g_round_ph[round_i][7] += (int)((m_ - clk_t) >> 10); clk_t = m_; }
 #endif
         IGT_TICK(11);
-        if (CTA_MLP) tc_candidates<T, COOP>(P, io, ws_base, sv.w, nl, n_try, n_spec, tc, coop_smem);   // value terms of all candidates, CTA-wide
-        if (trying) {
+        if (CTA_MLP) {
+            // Value terms CTA-wide, lazily: first every problem's first candidate (the one sequential halving tries
+            // first, accepted nine times out of ten); the speculative candidates only of the problems whose first
+            // was rejected.  Same candidates judged in the same order: same iterates.
+            const int left = P.n_alpha - sv.ls, nj = n_spec < left ? n_spec : left;
+            tc_candidates<T, COOP>(P, io, ws_base, sv.w, nl, n_try, 1, tc, coop_smem);
+            int tried = 0, jacc = -1;
+            if (trying) jacc = sv.judge_trials(0, 1, true, tried);
+            const bool more = trying && jacc < 0 && nj > 1;
+            if (trying) nl.more[my_idx] = more ? 1 : 0;
+            if (__syncthreads_or(more)) {
+                // candidates 1 .. n_spec-1: (n_spec - 1) n <= blockDim.x requests, one pass
+                tc_candidates<T, COOP>(P, io, ws_base, sv.w, nl, n_try, n_spec, tc, coop_smem, 1, true);
+                if (more) jacc = sv.judge_trials(1, nj, true, tried);
+            }
+            if (trying) sv.finish_trials(jacc, tried);
+        } else if (trying) {
             const int left = P.n_alpha - sv.ls;
-            sv.accept_trials(n_spec < left ? n_spec : left, CTA_MLP);
+            sv.accept_trials(n_spec < left ? n_spec : left, false);
         }
         IGT_TICK(8);
         if (active && sv.done) { sv.write_out(io, p); active = false; }
         IGT_TICK(10);
     }
 #ifdef IGT_PHASE_CLOCKS
+    if (threadIdx.x == 0 && blockIdx.x < 512) { g_cta_clk[blockIdx.x] = clock64() - cta_t0; g_cta_rounds[blockIdx.x] = cta_rounds; }
     if (clk_on) {
         for (int i = 0; i < 16; i++) g_phase_clk[i] = clk[i];
         for (int i = round_i; i < 512; i++) { g_round_clk[i] = 0; g_round_n[i] = -1; }

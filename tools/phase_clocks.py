@@ -36,6 +36,14 @@ print("B=%d ms=%.1f total cycles %.3e (%.1f ms @1.965GHz)" % (B, e0.elapsed_time
 for n, c in zip(names, clk):
     print("%-18s %12d  %5.1f%%" % (n, c, 100.0 * c / max(tot, 1)))
 
+if hasattr(lib, "igt_debug_cta_clocks"):
+    cc, cr = (C.c_longlong * 512)(), (C.c_int * 512)()
+    lib.igt_debug_cta_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    assert lib.igt_debug_cta_clocks(s._h, cc, cr) == 0
+    cc = np.array(cc[:148]) / 1.965e6; cr = np.array(cr[:148])
+    print("per CTA: ms from start to exit min %.1f median %.1f max %.1f; loop passes min %d median %d max %d; ms of the CTA with most passes %.1f"
+          % (cc.min(), np.median(cc), cc.max(), cr.min(), np.median(cr), cr.max(), cc[cr.argmax()]))
+
 if hasattr(lib, "igt_debug_round_clocks"):
     rc, rn = (C.c_longlong * 512)(), (C.c_int * 512)()
     lib.igt_debug_round_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
