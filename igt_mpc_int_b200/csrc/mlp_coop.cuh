@@ -35,14 +35,15 @@ constexpr int mlp_coop_smem_bytes(int block)
 template <typename T>
 __device__ __forceinline__ void coop_load_tile(T *tile, const T *Wt, int i0, int rows, int nout)
 {
-    const int total = rows * nout;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int ii = idx / nout, o = idx - ii * nout;
-        const unsigned d = (unsigned)__cvta_generic_to_shared(tile + ii * MLP_COOP_W + o);
-        const T *src = Wt + (long)(i0 + ii) * nout + o;
-        if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
-        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
-    }
+    // thread t copies column t % W of rows t / W, t / W + blockDim.x / W, ... (W = 128 divides the block: no division)
+    const int o = threadIdx.x & (MLP_COOP_W - 1), step = blockDim.x >> 7;
+    if (o < nout)
+        for (int ii = threadIdx.x >> 7; ii < rows; ii += step) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(tile + ii * MLP_COOP_W + o);
+            const T *src = Wt + (long)(i0 + ii) * nout + o;
+            if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+        }
     if ((rows & 1) && (int)threadIdx.x < MLP_COOP_W) tile[rows * MLP_COOP_W + threadIdx.x] = T(0);
 }
 
@@ -190,8 +191,15 @@ __device__ __noinline__ void mlp_coop_eval(const DevParams<T> &P, uint8_t *smem,
                 if (mine >= 0) {
                     const T *hi = act + e * COOP_ROWS * W;
                     T a = r == 0 ? b[0] : T(0);
-#pragma unroll 8
-                    for (int i = 0; i < nin; i++) a += wlast[i] * hi[r * W + i];
+                    int i = 0;
+                    for (; i + 16 <= nin; i += 16) {               // sixteen inputs' operands loaded ahead of their (ordered) FMAs
+                        T wv[16], hv[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) { wv[u] = wlast[i + u]; hv[u] = hi[r * W + i + u]; }
+#pragma unroll
+                        for (int u = 0; u < 16; u++) a += wv[u] * hv[u];
+                    }
+                    for (; i < nin; i++) a += wlast[i] * hi[r * W + i];
                     res[mine * COOP_ROWS + r] = r == 0 ? a * P.sigma_t + P.mu_t : a * P.sigma_t;
                 }
                 __syncwarp();
