@@ -106,3 +106,26 @@ def test_gt_mpc_full_size_batch_properties():
     for k in ("status", "iters", "cost", "u"):
         assert np.array_equal(rr[k][::-1], r[k], equal_nan=True), k
     s.close()
+
+
+@pytest.mark.parametrize("hidden,B", [((37, 65), 1000), ((128,), 19), ((5, 7, 3), 300), ((127, 128, 33), 517), ((16,), 1)])
+def test_cooperative_value_term_ragged_shapes(hidden, B):
+    """The CTA-cooperative evaluation streams the weights through shared memory in tiles of 16 inputs, two inputs per
+    pass, two evaluations per warp and wave: odd and short layers (padded tile rows), widths that are no multiple of 32,
+    batches that leave partial waves and warps without work -- bit-identical to the per-thread evaluation (same order of
+    operations) and equal to the oracle's forward tangents."""
+    from igt_mpc_int_b200.planner import BatchSolver
+    term = _term(_net(hidden, seed=7), True)
+    rng = np.random.default_rng(B)
+    sN, vN = rng.uniform(0, 70, B), rng.uniform(0, 5, B)
+    ctx = np.stack([rng.uniform(0, 70, B), rng.uniform(0, 5, B), rng.integers(-8, 9, B).astype(float),
+                    rng.integers(-8, 9, B).astype(float)], 1)
+    s = BatchSolver(N=40, mlp=_as_dict(term))
+    coop = s.mlp_value(sN, vN, ctx, tensor_cores=2)
+    per_thread = s.mlp_value(sN, vN, ctx, tensor_cores=0)
+    s.close()
+    assert np.array_equal(coop, per_thread)
+    n = min(B, 40)
+    ref = np.array([np.concatenate([[v], g, [H[0, 0], H[0, 1], H[1, 1]]]) for v, g, H in
+                    (term.value(sN[i], vN[i], ctx[i], order=2) for i in range(n))])
+    assert np.max(np.abs(coop[:n] - ref)) < 1e-11 * max(1.0, np.abs(ref).max())
