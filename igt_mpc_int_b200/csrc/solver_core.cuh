@@ -33,6 +33,9 @@
 #define IGT_HDN
 #endif
 
+#ifndef IGT_SB_RATIO
+#define IGT_SB_RATIO 0         // step bound: the binding row tracked as a (numerator, denominator) pair, one division per sweep
+#endif
 #ifndef IGT_PF_DIST
 #define IGT_PF_DIST 1          // stages ahead the latency-bound sweeps (adjoint, step bound) prefetch
 #endif
@@ -1457,6 +1460,9 @@ struct Solver {
         const int N = P.N, b = cur;
         const T tau = fmax(P.tau_min, T(1) - mu);
         T a = T(1), dz[NA];
+#if IGT_SB_RATIO
+        T an = T(1), ad = T(1);                                   // a = an / ad
+#endif
 #pragma unroll
         for (int i = 0; i < NA; i++) dz[i] = T(0);
         for (int k = 0; k <= N; k++) {
@@ -1487,7 +1493,13 @@ struct Solver {
                 if constexpr (i1 >= 0) dc += g1 * dw[i1];
                 if constexpr (i2 >= 0) dc += g2 * dw[i2];
                 T dy = -(c + y) - dc;
+#if IGT_SB_RATIO
+                const T ty = tau * y;
+                const bool tighter = dy < T(0) && -dy * an > ty * ad;
+                an = tighter ? ty : an; ad = tighter ? -dy : ad;
+#else
                 if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
+#endif
             });
             if (k == N - 1) {
 #pragma unroll 1
@@ -1503,7 +1515,13 @@ struct Solver {
                             T dc = A0 * dw[IV];
                             dc += A1 * dw[IUA];
                             T dy = -(c + y) - dc;
+#if IGT_SB_RATIO
+                            const T ty = tau * y;
+                            const bool tighter = dy < T(0) && -dy * an > ty * ad;
+                            an = tighter ? ty : an; ad = tighter ? -dy : ad;
+#else
                             if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
+#endif
                         }
                 }
             }
@@ -1516,6 +1534,9 @@ struct Solver {
                 dz[i] = acc;
             }
         }
+#if IGT_SB_RATIO
+        a = an / ad;
+#endif
         alpha = a * P.alpha_safety;
     }
 
