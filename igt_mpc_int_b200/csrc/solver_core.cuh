@@ -34,7 +34,7 @@
 #endif
 
 #ifndef IGT_SB_RATIO
-#define IGT_SB_RATIO 0         // step bound: the binding row tracked as a (numerator, denominator) pair, one division per sweep
+#define IGT_SB_RATIO 1         // step bound: the binding row tracked as a (numerator, denominator) pair, one division per sweep
 #endif
 #ifndef IGT_PF_DIST
 #define IGT_PF_DIST 1          // stages ahead the latency-bound sweeps (adjoint, step bound) prefetch
