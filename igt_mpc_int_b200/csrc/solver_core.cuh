@@ -1471,11 +1471,10 @@ struct Solver {
             // every load of the stage is issued up front (one exposed memory latency per stage, not one per row:
             // the rows below branch, so the compiler cannot hoist their loads itself)
             const int o = row_off(N, P.n_cinf, k), sb0 = slot_base(N, k);
-            T yv[NSLOT], F[NA][NW];
+            T yv[NSLOT];
 #pragma unroll
             for (int sl = 0; sl < NSLOT; sl++) if (slot_used(N, k, sl)) yv[sl] = w.Y(b, o + sl - sb0);
             load_z(b, k, z); load_up(b, k, up);
-            if (k < N) load_F(P, w, k, F);
 #pragma unroll
             for (int i = 0; i < NA; i++) dw[i] = dz[i];
             dw[IUA] = T(0); dw[IUD] = T(0);
@@ -1485,6 +1484,17 @@ struct Solver {
 #pragma unroll
                 for (int j = 0; j < NA; j++) { d0 += w.KK(k, 0, j) * dz[j]; d1 += w.KK(k, 1, j) * dz[j]; }
                 dw[IUA] = d0; dw[IUD] = d1;
+                // the next stage's state change right away: the 26 sensitivities are dead before the rows are visited
+                // (their registers were what this sweep spilled: 530 -> 338 bytes of spills in the kernel's main function)
+                T F[NA][NW];
+                load_F(P, w, k, F);
+#pragma unroll
+                for (int i = 0; i < NA; i++) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int j = 0; j < NW; j++) if (fmask(i, j)) acc += F[i][j] * dw[j];
+                    dz[i] = acc;
+                }
             }
             visit_rows<false, W::obca>(P, k, z, up, u, ox(k), oy(k), opsi(k), [&](auto SL, int, T c, auto I0, T g0, auto I1, T g1, auto I2, T g2, T, T, T) {
                 constexpr int sl = decltype(SL)::value, i0 = decltype(I0)::value, i1 = decltype(I1)::value, i2 = decltype(I2)::value;
@@ -1524,14 +1534,6 @@ struct Solver {
 #endif
                         }
                 }
-            }
-            if (k == N) break;
-#pragma unroll
-            for (int i = 0; i < NA; i++) {
-                T acc = T(0);
-#pragma unroll
-                for (int j = 0; j < NW; j++) if (fmask(i, j)) acc += F[i][j] * dw[j];
-                dz[i] = acc;
             }
         }
 #if IGT_SB_RATIO
