@@ -101,16 +101,22 @@ IGT_HD int row_total(int N, int n_cinf) { return row_off(N, n_cinf, N) + 3; }
 
 struct WsLayout {
     int N, M;
-    int oZ[NBUF], oU[NBUF], oY[NBUF], oS[NBUF], oTc, oSens, oLam, oKu, oKK, oGw, oRed, oGl, oHl, oTr, oDu, total;
+    // the NBUF iterate buffers of an array lie back to back: offset of buffer b = base + b * size (no table lookup with a
+    // run-time index, which would put the layout into local memory)
+    int oZ0, oU0, oY0, oS0, oTc, oSens, oLam, oKu, oKK, oGw, oRed, oGl, oHl, oTr, oDu, total;
+    IGT_HD int oZ(int b) const { return oZ0 + b * (NZ * (N + 1)); }
+    IGT_HD int oU(int b) const { return oU0 + b * (2 * N); }
+    IGT_HD int oY(int b) const { return oY0 + b * M; }
+    IGT_HD int oS(int b) const { return oS0 + b * M; }
     IGT_HD void init(int N_, int n_cinf, int nge = NGE, int nhe = NHE)
     {
         N = N_;
         M = row_total(N, n_cinf);
         int o = 0;
-        for (int b = 0; b < NBUF; b++) { oZ[b] = o; o += NZ * (N + 1); }
-        for (int b = 0; b < NBUF; b++) { oU[b] = o; o += 2 * N; }
-        for (int b = 0; b < NBUF; b++) { oY[b] = o; o += M; }
-        for (int b = 0; b < NBUF; b++) { oS[b] = o; o += M; }
+        oZ0 = o; o += NBUF * NZ * (N + 1);
+        oU0 = o; o += NBUF * 2 * N;
+        oY0 = o; o += NBUF * M;
+        oS0 = o; o += NBUF * M;
         oSens = o; o += NSENS * N;
         oLam = o;  o += NZ * (N + 1);
         oKu = o;   o += 2 * N;
@@ -151,11 +157,11 @@ struct Ws {
                 const unsigned ds = (unsigned)__cvta_generic_to_shared(rs + (2 * r) * rs_stride);
                 const unsigned dy = (unsigned)__cvta_generic_to_shared(rs + (2 * r + 1) * rs_stride);
                 if (sizeof(T) == 8) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ds), "l"(wb + (L.oS[b] + o + r) * STRIDE) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dy), "l"(wb + (L.oY[b] + o + r) * STRIDE) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ds), "l"(wb + (L.oS(b) + o + r) * STRIDE) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dy), "l"(wb + (L.oY(b) + o + r) * STRIDE) : "memory");
                 } else {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ds), "l"(wb + (L.oS[b] + o + r) * STRIDE) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dy), "l"(wb + (L.oY[b] + o + r) * STRIDE) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ds), "l"(wb + (L.oS(b) + o + r) * STRIDE) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dy), "l"(wb + (L.oY(b) + o + r) * STRIDE) : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -168,8 +174,8 @@ struct Ws {
         if (RSTG) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
     }
-    IGT_HD T row_s(int b, int o, int r) const { return RSTG ? rs[(2 * r) * rs_stride] : at(L.oS[b] + o + r); }
-    IGT_HD T row_y(int b, int o, int r) const { return RSTG ? rs[(2 * r + 1) * rs_stride] : at(L.oY[b] + o + r); }
+    IGT_HD T row_s(int b, int o, int r) const { return RSTG ? rs[(2 * r) * rs_stride] : at(L.oS(b) + o + r); }
+    IGT_HD T row_y(int b, int o, int r) const { return RSTG ? rs[(2 * r + 1) * rs_stride] : at(L.oY(b) + o + r); }
     static constexpr int nge = OBCA ? NGE_OBCA : NGE, nhe = OBCA ? NHE_OBCA : NHE;
     T *wb;          // base + (slot / 32) * total * 32 + slot % 32
     WsLayout L;
@@ -182,10 +188,10 @@ struct Ws {
         if (STRIDE == 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + e * 32));
 #endif
     }
-    IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ[b] + k * NZ + i); }
-    IGT_HD T &U(int b, int k, int i) const { return at(L.oU[b] + k * 2 + i); }
-    IGT_HD T &Y(int b, int r) const { return at(L.oY[b] + r); }
-    IGT_HD T &S(int b, int r) const { return at(L.oS[b] + r); }
+    IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ(b) + k * NZ + i); }
+    IGT_HD T &U(int b, int k, int i) const { return at(L.oU(b) + k * 2 + i); }
+    IGT_HD T &Y(int b, int r) const { return at(L.oY(b) + r); }
+    IGT_HD T &S(int b, int r) const { return at(L.oS(b) + r); }
     IGT_HD T &Sens(int k, int e) const { return at(L.oSens + k * NSENS + e); }
     IGT_HD T &Lam(int k, int i) const { return at(L.oLam + k * NZ + i); }
     IGT_HD T &ku(int k, int i) const { return at(L.oKu + k * 2 + i); }
@@ -641,13 +647,13 @@ IGT_HD void prefetch_rows(const DevParams<T> &P, const W &w, int k, int b, int o
     if (W::rstg) {                                               // (the terminal-set rows of node N-1 are loaded in place)
         w.rows_fetch(b, o, ns);
         if (k == P.N - 1)
-            for (int r = ns; r < ns + P.n_cinf; r++) { w.pf(w.L.oY[b] + o + r); if (WANT_S) w.pf(w.L.oS[b] + o + r); }
+            for (int r = ns; r < ns + P.n_cinf; r++) { w.pf(w.L.oY(b) + o + r); if (WANT_S) w.pf(w.L.oS(b) + o + r); }
         return;
     }
     const int n = ns + (k == P.N - 1 ? P.n_cinf : 0);
     for (int r = 0; r < n; r++) {
-        w.pf(w.L.oY[b] + o + r);
-        if (WANT_S) w.pf(w.L.oS[b] + o + r);
+        w.pf(w.L.oY(b) + o + r);
+        if (WANT_S) w.pf(w.L.oS(b) + o + r);
     }
 }
 
@@ -925,8 +931,8 @@ IGT_HD void rollout_item(const DevParams<T> &P, const W &w, const NodeCtx<T> &c,
         T dw[NA];
         if (k + 1 < N) {
 #pragma unroll
-            for (int i = 0; i < NZ; i++) w.pf(w.L.oZ[b] + (k + 1) * NZ + i);
-            w.pf(w.L.oU[b] + (k + 1) * 2); w.pf(w.L.oU[b] + (k + 1) * 2 + 1);
+            for (int i = 0; i < NZ; i++) w.pf(w.L.oZ(b) + (k + 1) * NZ + i);
+            w.pf(w.L.oU(b) + (k + 1) * 2); w.pf(w.L.oU(b) + (k + 1) * 2 + 1);
             w.pf(w.L.oKu + (k + 1) * 2); w.pf(w.L.oKu + (k + 1) * 2 + 1);
 #pragma unroll
             for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + (k + 1) * 2 * NA + i);
@@ -1076,12 +1082,12 @@ struct Solver {
     {
         if (k < 0 || k > P.N) return;
 #pragma unroll
-        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ[b] + k * NZ + i);
-        if (k < P.N) { w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1); }
+        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ(b) + k * NZ + i);
+        if (k < P.N) { w.pf(w.L.oU(b) + k * 2); w.pf(w.L.oU(b) + k * 2 + 1); }
         if (rows) {
             const int o = row_off(P.N, P.n_cinf, k);
             const int n = (k == 0) ? 8 : (k == P.N ? 3 : 13);
-            for (int r = 0; r < n; r++) { w.pf(w.L.oY[b] + o + r); w.pf(w.L.oS[b] + o + r); }
+            for (int r = 0; r < n; r++) { w.pf(w.L.oY(b) + o + r); w.pf(w.L.oS(b) + o + r); }
         }
         if (sens && k < P.N) {
 #pragma unroll
@@ -1101,12 +1107,12 @@ struct Solver {
     {
         if (k > P.N) return;
 #pragma unroll
-        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ[b] + k * NZ + i);
+        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ(b) + k * NZ + i);
         const int o = row_off(P.N, P.n_cinf, k);
         const int n = (k == 0) ? 8 : (k == P.N ? 3 : 13);
-        for (int r = 0; r < n; r++) w.pf(w.L.oY[b] + o + r);
+        for (int r = 0; r < n; r++) w.pf(w.L.oY(b) + o + r);
         if (k == P.N) return;
-        w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1);
+        w.pf(w.L.oU(b) + k * 2); w.pf(w.L.oU(b) + k * 2 + 1);
         w.pf(w.L.oKu + k * 2); w.pf(w.L.oKu + k * 2 + 1);
 #pragma unroll
         for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
@@ -1120,8 +1126,8 @@ struct Solver {
         if (k < 0) return;
 #pragma unroll
         for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
-        w.pf(w.L.oZ[b] + k * NZ + IEY); w.pf(w.L.oZ[b] + k * NZ + IEPSI);
-        w.pf(w.L.oU[b] + k * 2); w.pf(w.L.oU[b] + k * 2 + 1);
+        w.pf(w.L.oZ(b) + k * NZ + IEY); w.pf(w.L.oZ(b) + k * NZ + IEPSI);
+        w.pf(w.L.oU(b) + k * 2); w.pf(w.L.oU(b) + k * 2 + 1);
         if (riccati) {
 #pragma unroll
             for (int e = 0; e < W::nge; e++) w.pf(w.L.oGl + k * W::nge + e);
