@@ -188,6 +188,20 @@ struct Ws {
         if (STRIDE == 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + e * 32));
 #endif
     }
+    // NN consecutive elements from e0: one address computation, then immediate offsets (a prefetch with its own index
+    // costs five integer instructions on top of the prefetch itself)
+    template <int I, int NN>
+    IGT_HD void pf_run_(const T *base) const
+    {
+#ifdef __CUDA_ARCH__
+        if constexpr (I < NN) {
+            asm volatile("prefetch.global.L1 [%0+%1];" ::"l"(base), "n"(I * 32 * (int)sizeof(T)));
+            pf_run_<I + 1, NN>(base);
+        }
+#endif
+    }
+    template <int NN>
+    IGT_HD void pf_run(int e0) const { if (STRIDE == 32) pf_run_<0, NN>(wb + e0 * 32); }
     IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ(b) + k * NZ + i); }
     IGT_HD T &U(int b, int k, int i) const { return at(L.oU(b) + k * 2 + i); }
     IGT_HD T &Y(int b, int r) const { return at(L.oY(b) + r); }
@@ -930,12 +944,10 @@ IGT_HD void rollout_item(const DevParams<T> &P, const W &w, const NodeCtx<T> &c,
     for (int k = 0; k < N; k++) {
         T dw[NA];
         if (k + 1 < N) {
-#pragma unroll
-            for (int i = 0; i < NZ; i++) w.pf(w.L.oZ(b) + (k + 1) * NZ + i);
-            w.pf(w.L.oU(b) + (k + 1) * 2); w.pf(w.L.oU(b) + (k + 1) * 2 + 1);
-            w.pf(w.L.oKu + (k + 1) * 2); w.pf(w.L.oKu + (k + 1) * 2 + 1);
-#pragma unroll
-            for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + (k + 1) * 2 * NA + i);
+            w.template pf_run<NZ>(w.L.oZ(b) + (k + 1) * NZ);
+            w.template pf_run<2>(w.L.oU(b) + (k + 1) * 2);
+            w.template pf_run<2>(w.L.oKu + (k + 1) * 2);
+            w.template pf_run<2 * NA>(w.L.oKK + (k + 1) * 2 * NA);
         }
 #pragma unroll
         for (int i = 0; i < NZ; i++) dw[i] = zn[i] - w.Z(b, k, i);
@@ -1081,24 +1093,20 @@ struct Solver {
     IGT_HD void prefetch_stage(int b, int k, bool rows, bool sens, bool gains) const
     {
         if (k < 0 || k > P.N) return;
-#pragma unroll
-        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ(b) + k * NZ + i);
-        if (k < P.N) { w.pf(w.L.oU(b) + k * 2); w.pf(w.L.oU(b) + k * 2 + 1); }
+        w.template pf_run<NZ>(w.L.oZ(b) + k * NZ);
+        if (k < P.N) { w.template pf_run<2>(w.L.oU(b) + k * 2); }
         if (rows) {
             const int o = row_off(P.N, P.n_cinf, k);
             const int n = (k == 0) ? 8 : (k == P.N ? 3 : 13);
             for (int r = 0; r < n; r++) { w.pf(w.L.oY(b) + o + r); w.pf(w.L.oS(b) + o + r); }
         }
         if (sens && k < P.N) {
-#pragma unroll
-            for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
-#pragma unroll
-            for (int i = 0; i < NZ; i++) w.pf(w.L.oLam + (k + 1) * NZ + i);
+            w.template pf_run<NSENS>(w.L.oSens + k * NSENS);
+            w.template pf_run<NZ>(w.L.oLam + (k + 1) * NZ);
         }
         if (gains && k < P.N) {
-            w.pf(w.L.oKu + k * 2); w.pf(w.L.oKu + k * 2 + 1);
-#pragma unroll
-            for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + k * 2 * NA + i);
+            w.template pf_run<2>(w.L.oKu + k * 2);
+            w.template pf_run<2 * NA>(w.L.oKK + k * 2 * NA);
         }
     }
 
@@ -1106,38 +1114,29 @@ struct Solver {
     IGT_HD void prefetch_bound(int b, int k) const
     {
         if (k > P.N) return;
-#pragma unroll
-        for (int i = 0; i < NZ; i++) w.pf(w.L.oZ(b) + k * NZ + i);
+        w.template pf_run<NZ>(w.L.oZ(b) + k * NZ);
         const int o = row_off(P.N, P.n_cinf, k);
-        const int n = (k == 0) ? 8 : (k == P.N ? 3 : 13);
-        for (int r = 0; r < n; r++) w.pf(w.L.oY(b) + o + r);
+        w.template pf_run<NSLOT>(w.L.oY(b) + o);                 // (first and last node: a few words of the next node as well)
         if (k == P.N) return;
-        w.pf(w.L.oU(b) + k * 2); w.pf(w.L.oU(b) + k * 2 + 1);
-        w.pf(w.L.oKu + k * 2); w.pf(w.L.oKu + k * 2 + 1);
-#pragma unroll
-        for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
-#pragma unroll
-        for (int i = 0; i < 2 * NA; i++) w.pf(w.L.oKK + k * 2 * NA + i);
+        w.template pf_run<2>(w.L.oU(b) + k * 2);
+        w.template pf_run<2>(w.L.oKu + k * 2);
+        w.template pf_run<NSENS>(w.L.oSens + k * NSENS);
+        w.template pf_run<2 * NA>(w.L.oKK + k * 2 * NA);
     }
 
     // next stage of the backward sweeps: sensitivities, node summaries, the few iterate entries used
     IGT_HD void prefetch_back(int b, int k, bool riccati) const
     {
         if (k < 0) return;
-#pragma unroll
-        for (int i = 0; i < NSENS; i++) w.pf(w.L.oSens + k * NSENS + i);
-        w.pf(w.L.oZ(b) + k * NZ + IEY); w.pf(w.L.oZ(b) + k * NZ + IEPSI);
-        w.pf(w.L.oU(b) + k * 2); w.pf(w.L.oU(b) + k * 2 + 1);
+        w.template pf_run<NSENS>(w.L.oSens + k * NSENS);
+        w.template pf_run<2>(w.L.oZ(b) + k * NZ + IEY);
+        w.template pf_run<2>(w.L.oU(b) + k * 2);
         if (riccati) {
-#pragma unroll
-            for (int e = 0; e < W::nge; e++) w.pf(w.L.oGl + k * W::nge + e);
-#pragma unroll
-            for (int e = 0; e < W::nhe; e++) w.pf(w.L.oHl + k * W::nhe + e);
+            w.template pf_run<W::nge>(w.L.oGl + k * W::nge);
+            w.template pf_run<W::nhe>(w.L.oHl + k * W::nhe);
         } else {
-#pragma unroll
-            for (int e = 0; e < W::nge; e++) w.pf(w.L.oGw + k * W::nge + e);
-#pragma unroll
-            for (int e = 0; e < 4; e++) w.pf(w.L.oRed + k * 4 + e);
+            w.template pf_run<W::nge>(w.L.oGw + k * W::nge);
+            w.template pf_run<4>(w.L.oRed + k * 4);
         }
     }
 
