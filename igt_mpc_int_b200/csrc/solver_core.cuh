@@ -1088,28 +1088,6 @@ struct Solver {
         }
     }
 
-    // software prefetch of stage k's workspace rows (the sweeps stream ~1.6 GB of workspace per
-    // launch; issuing the next stage's lines early hides most of the HBM/L2 latency)
-    IGT_HD void prefetch_stage(int b, int k, bool rows, bool sens, bool gains) const
-    {
-        if (k < 0 || k > P.N) return;
-        w.template pf_run<NZ>(w.L.oZ(b) + k * NZ);
-        if (k < P.N) { w.template pf_run<2>(w.L.oU(b) + k * 2); }
-        if (rows) {
-            const int o = row_off(P.N, P.n_cinf, k);
-            const int n = (k == 0) ? 8 : (k == P.N ? 3 : 13);
-            for (int r = 0; r < n; r++) { w.pf(w.L.oY(b) + o + r); w.pf(w.L.oS(b) + o + r); }
-        }
-        if (sens && k < P.N) {
-            w.template pf_run<NSENS>(w.L.oSens + k * NSENS);
-            w.template pf_run<NZ>(w.L.oLam + (k + 1) * NZ);
-        }
-        if (gains && k < P.N) {
-            w.template pf_run<2>(w.L.oKu + k * 2);
-            w.template pf_run<2 * NA>(w.L.oKK + k * 2 * NA);
-        }
-    }
-
     // stage k of the step-bound sweep: iterate, slacks (not the multipliers), sensitivities, gains
     IGT_HD void prefetch_bound(int b, int k) const
     {
