@@ -189,7 +189,7 @@ int igt_mlp_value_host(igt_handle *h, int B, const double *sN, const double *vN,
 
 /* Run-time switches.
  * "tensor_core_mlp" (default 0).  The gt_mpc value term is evaluated exactly (fp64) by default, CTA-cooperatively
- * (csrc/mlp_coop.cuh: one warp per evaluation, any network up to 128 wide -- all eight shipped V_GT_sc*.pt).  1 = the
+ * (csrc/mlp_coop.cuh: waves of 16 evaluations, weights streamed through shared memory, any network up to 128 wide -- all eight shipped V_GT_sc*.pt).  1 = the
  * tcgen05 kernel (csrc/mlp_tc.cuh; 6-128-128-1 networks, bf16x3 = fp32-accurate): measured no faster than the exact
  * path on a B200 and it perturbs the merit at 1e-7, so closed-loop outcomes can differ from the
  * fp64 oracle's; kept as an option.
