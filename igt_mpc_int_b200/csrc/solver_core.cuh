@@ -147,6 +147,7 @@ template <typename T, int STRIDE = 32, bool OBCA = false, bool RSTG = false>
 struct Ws {
     static constexpr bool obca = OBCA;
     static constexpr bool rstg = RSTG;
+    static constexpr int stride = STRIDE;
     T *rs = nullptr;                     // RSTG: this thread's column, slot i at rs[i * blockDim.x]
     int rs_stride = 0;
     IGT_HD void rows_fetch(int b, int o, int n) const
@@ -202,6 +203,10 @@ struct Ws {
     }
     template <int NN>
     IGT_HD void pf_run(int e0) const { if (STRIDE == 32) pf_run_<0, NN>(wb + e0 * 32); }
+    // pointer to element e0; element e0 + i is p[i * STRIDE] -- with a compile-time i the offset folds into the load /
+    // store instruction (used in the node phases and in the rollout, functions with registers to spare: every workspace
+    // access there used to carry five integer instructions of address arithmetic)
+    IGT_HD T *ptr(int e0) const { return wb + (long)e0 * STRIDE; }
     IGT_HD T &Z(int b, int k, int i) const { return at(L.oZ(b) + k * NZ + i); }
     IGT_HD T &U(int b, int k, int i) const { return at(L.oU(b) + k * 2 + i); }
     IGT_HD T &Y(int b, int r) const { return at(L.oY(b) + r); }
@@ -810,11 +815,13 @@ template <typename T, typename W>
 IGT_HD void node_load(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, int k, T *z, T *up, T *u)
 {
     const int b = c.cur;
+    constexpr int S = W::stride;
+    const T *pz = w.ptr(w.L.oZ(b) + k * NZ), *pu = w.ptr(w.L.oU(b) + k * 2);
 #pragma unroll
-    for (int i = 0; i < NZ; i++) z[i] = w.Z(b, k, i);
+    for (int i = 0; i < NZ; i++) z[i] = pz[i * S];
     if (k == 0) { up[0] = c.uprev[0]; up[1] = c.uprev[1]; }
-    else { up[0] = w.U(b, k - 1, 0); up[1] = w.U(b, k - 1, 1); }
-    if (k < P.N) { u[0] = w.U(b, k, 0); u[1] = w.U(b, k, 1); } else { u[0] = u[1] = T(0); }
+    else { up[0] = pu[-2 * S]; up[1] = pu[-1 * S]; }
+    if (k < P.N) { u[0] = pu[0]; u[1] = pu[S]; } else { u[0] = u[1] = T(0); }
 }
 
 // Node phase 1 (independent of the barrier parameter and of the adjoint): sensitivities of stage k
@@ -831,8 +838,9 @@ IGT_HD void node_phase1(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
     if (k < N) {
         T zn[NZ], Sc[NSENS];
         rk4_step_sens(P, z, u, c.curv, zn, Sc);
+        { T *ps = w.ptr(w.L.oSens + k * NSENS);
 #pragma unroll
-        for (int e = 0; e < NSENS; e++) w.Sens(k, e) = Sc[e];
+          for (int e = 0; e < NSENS; e++) ps[e * W::stride] = Sc[e]; }
     }
     T gw[NW];
 #pragma unroll
@@ -861,8 +869,8 @@ IGT_HD void node_phase1(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
             sy_min = fmin(sy_min, sy); sy_max = fmax(sy_max, sy);
         });
 #pragma unroll
-    for (int e = 0; e < W::nge; e++) w.Gw(k, e) = gw[ge_idx(e)];
-    w.Red(k, 0) = rp; w.Red(k, 1) = s_max; w.Red(k, 2) = sy_min; w.Red(k, 3) = sy_max;
+    for (int e = 0; e < W::nge; e++) w.ptr(w.L.oGw + k * W::nge)[e * W::stride] = gw[ge_idx(e)];
+    { T *pr = w.ptr(w.L.oRed + k * 4); pr[0] = rp; pr[W::stride] = s_max; pr[2 * W::stride] = sy_min; pr[3 * W::stride] = sy_max; }
 }
 
 // Node phase 2 (after the barrier update and the adjoint sweep): the rows' share of the perturbed
@@ -885,7 +893,7 @@ IGT_HD void node_phase2(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
     if (k < N && c.second_order) {
         T ln[NZ];
 #pragma unroll
-        for (int i = 0; i < NZ; i++) ln[i] = w.Lam(k + 1, i);
+        for (int i = 0; i < NZ; i++) ln[i] = w.ptr(w.L.oLam + (k + 1) * NZ)[i * W::stride];
         add_dyn_hessian(P, z, u, c.curv, ln, H);
     }
     w.rows_wait();
@@ -922,9 +930,9 @@ IGT_HD void node_phase2(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
             H[sym11(IV, IUA)] += sig * A0 * A1;
         });
 #pragma unroll
-    for (int e = 0; e < W::nge; e++) w.Gl(k, e) = g[ge_idx(e)];
+    for (int e = 0; e < W::nge; e++) w.ptr(w.L.oGl + k * W::nge)[e * W::stride] = g[ge_idx(e)];
 #pragma unroll
-    for (int e = 0; e < W::nhe; e++) w.Hl(k, e) = H[sym11(he_i(e), he_j(e))];
+    for (int e = 0; e < W::nhe; e++) w.ptr(w.L.oHl + k * W::nhe)[e * W::stride] = H[sym11(he_i(e), he_j(e))];
 }
 
 // Closed-loop nonlinear rollout of candidate j of the line search (step alpha / 2^j) from the
@@ -949,23 +957,27 @@ IGT_HD void rollout_item(const DevParams<T> &P, const W &w, const NodeCtx<T> &c,
             w.template pf_run<2>(w.L.oKu + (k + 1) * 2);
             w.template pf_run<2 * NA>(w.L.oKK + (k + 1) * 2 * NA);
         }
+        constexpr int S = W::stride;
+        const T *pz = w.ptr(w.L.oZ(b) + k * NZ), *pu = w.ptr(w.L.oU(b) + k * 2), *pk = w.ptr(w.L.oKu + k * 2),
+                *pK = w.ptr(w.L.oKK + k * 2 * NA);
+        T *qu = w.ptr(w.L.oU(nb) + k * 2), *qd = w.ptr(w.L.oDu + (nb * N + k) * 2), *qz = w.ptr(w.L.oZ(nb) + (k + 1) * NZ);
 #pragma unroll
-        for (int i = 0; i < NZ; i++) dw[i] = zn[i] - w.Z(b, k, i);
+        for (int i = 0; i < NZ; i++) dw[i] = zn[i] - pz[i * S];
         if (k == 0) { dw[IPA] = T(0); dw[IPD] = T(0); }
-        else { dw[IPA] = upn[0] - w.U(b, k - 1, 0); dw[IPD] = upn[1] - w.U(b, k - 1, 1); }
-        T d0 = alpha * w.ku(k, 0), d1 = alpha * w.ku(k, 1);
+        else { dw[IPA] = upn[0] - pu[-2 * S]; dw[IPD] = upn[1] - pu[-1 * S]; }
+        T d0 = alpha * pk[0], d1 = alpha * pk[S];
 #pragma unroll
-        for (int i = 0; i < NA; i++) { d0 += w.KK(k, 0, i) * dw[i]; d1 += w.KK(k, 1, i) * dw[i]; }
-        T un[2] = { w.U(b, k, 0) + d0, w.U(b, k, 1) + d1 };
+        for (int i = 0; i < NA; i++) { d0 += pK[i * S] * dw[i]; d1 += pK[(NA + i) * S] * dw[i]; }
+        T un[2] = { pu[0] + d0, pu[S] + d1 };
         J += zn[IEPSI] * zn[IEPSI] + zn[IEY] * zn[IEY];
         su += un[0] * un[0] + un[1] * un[1];
-        w.U(nb, k, 0) = un[0]; w.U(nb, k, 1) = un[1];
-        w.Du(nb, k, 0) = d0; w.Du(nb, k, 1) = d1;
+        qu[0] = un[0]; qu[S] = un[1];
+        qd[0] = d0; qd[S] = d1;
         T zz[NZ];
         rk4_step(P, zn, un, c.curv, zz);
         bool fin = true;
 #pragma unroll
-        for (int i = 0; i < NZ; i++) { zn[i] = zz[i]; w.Z(nb, k + 1, i) = zz[i]; fin = fin && (zz[i] == zz[i]) && fabs(zz[i]) < T(1e15); }
+        for (int i = 0; i < NZ; i++) { zn[i] = zz[i]; qz[i * S] = zz[i]; fin = fin && (zz[i] == zz[i]) && fabs(zz[i]) < T(1e15); }
         if (!fin) { fail = true; break; }
         upn[0] = un[0]; upn[1] = un[1];
     }
