@@ -33,9 +33,6 @@
 #define IGT_HDN
 #endif
 
-#ifndef IGT_SB_RATIO
-#define IGT_SB_RATIO 1         // step bound: the binding row tracked as a (numerator, denominator) pair, one division per sweep
-#endif
 #ifndef IGT_PF_DIST
 #define IGT_PF_DIST 1          // stages ahead the latency-bound sweeps (adjoint, step bound) prefetch
 #endif
@@ -1002,13 +999,16 @@ IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
     const T mu = c.mu, tau = fmax(P.tau_min, T(1) - mu);
     T z[NZ], up[2], u[2], zn[NZ], upn[2], un[2], dw[NW];
     node_load(P, w, c, k, z, up, u);
+    constexpr int S = W::stride;
+    const T *qz = w.ptr(w.L.oZ(nb) + k * NZ), *qu = w.ptr(w.L.oU(nb) + k * 2), *qd = w.ptr(w.L.oDu + (nb * N + k) * 2);
 #pragma unroll
-    for (int i = 0; i < NZ; i++) { zn[i] = w.Z(nb, k, i); dw[i] = zn[i] - z[i]; }
+    for (int i = 0; i < NZ; i++) { zn[i] = qz[i * S]; dw[i] = zn[i] - z[i]; }
     if (k == 0) { upn[0] = c.uprev[0]; upn[1] = c.uprev[1]; }
-    else { upn[0] = w.U(nb, k - 1, 0); upn[1] = w.U(nb, k - 1, 1); }
-    if (k < N) { un[0] = w.U(nb, k, 0); un[1] = w.U(nb, k, 1); } else { un[0] = un[1] = T(0); }
+    else { upn[0] = qu[-2 * S]; upn[1] = qu[-1 * S]; }
+    if (k < N) { un[0] = qu[0]; un[1] = qu[S]; } else { un[0] = un[1] = T(0); }
     dw[IPA] = upn[0] - up[0]; dw[IPD] = upn[1] - up[1];
-    if (k < N) { dw[IUA] = w.Du(nb, k, 0); dw[IUD] = w.Du(nb, k, 1); } else { dw[IUA] = dw[IUD] = T(0); }
+    if (k < N) { dw[IUA] = qd[0]; dw[IUD] = qd[S]; } else { dw[IUA] = dw[IUD] = T(0); }
+    T *py = w.ptr(w.L.oY(nb) + o), *ps = w.ptr(w.L.oS(nb) + o);      // rows of the trial point: row r at py[r * S]
     const T ox = T(c.obs[2 * k]), oy = T(c.obs[2 * k + 1]), opsi = W::obca ? T(c.obs_psi[k]) : T(0);
     bool fail = false;
     T ynv[NSLOT];
@@ -1024,7 +1024,7 @@ IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
         if (yn < (T(1) - tau) * y) fail = true;                 // fraction to the boundary
         sn = fmax(sn, (T(1) - tau) * s);                        // multiplier safeguard
         ynv[sl] = yn;
-        w.Y(nb, o + r) = yn; w.S(nb, o + r) = sn;
+        py[r * S] = yn; ps[r * S] = sn;
     });
     // infeasibility and barrier sum at the trial point: the stage rows first, then (stage N-1) the
     // terminal-set rows, whose update along the step and value at the new point share one loop
@@ -1048,7 +1048,7 @@ IGT_HD void node_phase3(const DevParams<T> &P, const W &w, const NodeCtx<T> &c, 
             w.Y(nb, r) = yn; w.S(nb, r) = sn;
             if (!fail) { th += fabs(A0 * zn[IV] + A1 * un[0] - bb + yn); lg.add(yn); }
         });
-    w.Tr(nb, k, 0) = th; w.Tr(nb, k, 1) = fail ? T(0) : lg.total(); w.Tr(nb, k, 2) = fail ? T(1) : T(0);
+    { T *pt = w.ptr(w.L.oTr + (nb * (N + 1) + k) * 3); pt[0] = th; pt[S] = fail ? T(0) : lg.total(); pt[2 * S] = fail ? T(1) : T(0); }
 }
 
 // ------------------------------------------------------------------ the solver ---------
@@ -1454,10 +1454,10 @@ struct Solver {
     {
         const int N = P.N, b = cur;
         const T tau = fmax(P.tau_min, T(1) - mu);
-        T a = T(1), dz[NA];
-#if IGT_SB_RATIO
-        T an = T(1), ad = T(1);                                   // a = an / ad
-#endif
+        // the binding row is kept as a (numerator, denominator) pair updated with selects and divided once at the end:
+        // a branch with an inlined fp64 division behind every row (taken by some lane of a warp almost always) cost a
+        // third of this sweep's instructions
+        T an = T(1), ad = T(1), dz[NA];
 #pragma unroll
         for (int i = 0; i < NA; i++) dz[i] = T(0);
         for (int k = 0; k <= N; k++) {
@@ -1498,13 +1498,9 @@ struct Solver {
                 if constexpr (i1 >= 0) dc += g1 * dw[i1];
                 if constexpr (i2 >= 0) dc += g2 * dw[i2];
                 T dy = -(c + y) - dc;
-#if IGT_SB_RATIO
                 const T ty = tau * y;
                 const bool tighter = dy < T(0) && -dy * an > ty * ad;
                 an = tighter ? ty : an; ad = tighter ? -dy : ad;
-#else
-                if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
-#endif
             });
             if (k == N - 1) {
 #pragma unroll 1
@@ -1520,21 +1516,14 @@ struct Solver {
                             T dc = A0 * dw[IV];
                             dc += A1 * dw[IUA];
                             T dy = -(c + y) - dc;
-#if IGT_SB_RATIO
                             const T ty = tau * y;
                             const bool tighter = dy < T(0) && -dy * an > ty * ad;
                             an = tighter ? ty : an; ad = tighter ? -dy : ad;
-#else
-                            if (dy < T(0) && -dy * a > tau * y) a = tau * y / (-dy);
-#endif
                         }
                 }
             }
         }
-#if IGT_SB_RATIO
-        a = an / ad;
-#endif
-        alpha = a * P.alpha_safety;
+        alpha = (an / ad) * P.alpha_safety;
     }
 
     // The backward pass is split so that the kernels can run the node-local work of all stages of
