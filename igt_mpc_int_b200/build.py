@@ -8,8 +8,8 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(_HERE, "csrc", f) for f in ("igt_abi.cu",)]
-DEPS = SRC + [os.path.join(_HERE, "csrc", f) for f in ("solver_core.cuh", "params_host.hpp", "mlp_tc.cuh", "obca.cuh")] + \
-       [os.path.join(_HERE, "..", "include", "igt_mpc.h")]
+DEPS = sorted(os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))
+              if f.endswith((".cu", ".cuh", ".hpp"))) + [os.path.join(_HERE, "..", "include", "igt_mpc.h")]
 OUT = os.path.join(_HERE, "lib", "libigtmpc.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
