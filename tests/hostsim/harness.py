@@ -15,7 +15,7 @@ _dp = C.POINTER(C.c_double)
 def build():
     src = os.path.join(_HERE, "hostsim.cu")
     deps = [src] + [os.path.join(_HERE, "..", "..", "igt_mpc_int_b200", "csrc", f)
-                    for f in ("solver_core.cuh", "params_host.hpp", "obca.cuh")]
+                    for f in ("solver_core.cuh", "params_host.hpp", "obca.cuh", "mlp_coop.cuh", "mlp_tc.cuh")]
     if not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
                                "-Xcompiler", "-fPIC", "-shared", "-o", _SO, src])
