@@ -2,6 +2,7 @@
 # the round-end evidence run: per-CTA / per-round clocks (debug build), thin-regime and overhead probes, ncu launch list of bench.py,
 # ncu --set full captures of the solver kernel and of the cooperative value-term kernel, FP64 instruction counts.  usage: tools/final_profiles.sh (on the GPU box)
 set -x
+[ -f build/libigtmpc_clk.so ] || tools/build_variant.sh clk -DIGT_PHASE_CLOCKS     # debug build with the cycle counters
 python tools/phase_clocks.py build/libigtmpc_clk.so 32768 > gpurun_out/r2f_clk_cfg2.log 2>&1
 python tools/thin_probe.py 148 0 3 > gpurun_out/r2f_thin.log 2>&1; python tools/thin_probe.py 148 1 3 >> gpurun_out/r2f_thin.log 2>&1
 python tools/overhead_probe.py >> gpurun_out/r2f_thin.log 2>&1
