@@ -1152,12 +1152,15 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NZ; i++) z[i] = x0[i];
         J += z[IEPSI] * z[IEPSI] + z[IEY] * z[IEY];
+        // the feed-forward steering angle takes two values along a route (pw_const curvature): the one of the arc is
+        // computed once per rollout instead of three transcendental calls per step
+        const T dff_arc = atan(T(2) * tan(asin(curv[2] * P.l_r)));
         for (int k = 0; k < N; k++) {
             T K = curvature(z[IS], curv[0], curv[1], curv[2]);
             T a = T(0.5) * (vt - z[IV]);
             a = fmin(fmax(a, up[0] - P.da_max), up[0] + P.da_max);
             a = fmin(fmax(a, P.a_min), P.a_max);
-            T dff = atan(T(2) * tan(asin(K * P.l_r)));
+            T dff = K == T(0) ? T(0) : (K == curv[2] ? dff_arc : atan(T(2) * tan(asin(K * P.l_r))));
             T d = dff - T(0.3) * z[IEY] - T(0.8) * z[IEPSI];
             d = fmin(fmax(d, up[1] - P.ddf_max), up[1] + P.ddf_max);
             d = fmin(fmax(d, -P.df_max), P.df_max);
